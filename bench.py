@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the MoTIF per-pixel inference hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path (Ours.py:659-858: gather -> imnet/flow_imnet -> 3 splats x 2
+references -> blend -> synth_net -> clamp) over one synthetic Adobe240-shaped clip
+(180x320 -> 720x1280, 7 intermediate timestamps) from resident LR latents.  `value` is output
+pixel-timestamps per second of the whole job, inputs resident in HBM; `e2e` is the same through the
+public API (`SpaceTimeDecoder.decode`) with pinned HOST latents copied in and the frames copied out
+inside the timed region.  With N > 1 ranks (torchrun) rank 0 owns the latents, broadcasts them over
+NCCL inside every step (the path's one exchange) and each rank decodes its own timestamps.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "hr_output_pixels_per_sec"
+UNIT = "px-t/s"
+
+# algorithmic work per unit (BASELINE.md section 3 / SURVEY.md 8d)
+FLOP_FLOW_IMNET_ROW = 2 * 25536  # per (reference, pixel, timestamp)
+FLOP_IMNET_ROW = 2 * 41088       # per (reference, pixel)
+FLOP_SYNTH_ROW = 2 * 38016       # per (pixel, timestamp)
+SPLAT_BYTES_PER_SRC = 1056       # softmax splat, C=130: 4*(2C+4)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(workload, steps, warmup, sample_note):
+    """The reference's CPU implementation of the path (oracle port of Ours.py:659-858 with the cupy
+    splats transcribed to index_add_), all host threads, on a bounded sample of the workload."""
+    from motif_b200 import synthetic
+    from oracle import decoder_ref
+
+    H, W, HH, WW, times = workload
+    torch.set_num_threads(os.cpu_count() or 1)
+    feat, ff, res = synthetic.synthetic_latents(1, H, W, seed=0)
+    params = synthetic.synthetic_params(seed=0)
+    tt = torch.tensor([times])
+    durations = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        decoder_ref.decode(feat, ff, res, tt, HH, WW, params)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            durations.append(dt)
+    total = sum(durations)
+    units = len(times) * HH * WW * len(durations)
+    return {"value": units / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample_note,
+            "ms_per_step": 1e3 * total / len(durations)}
+
+
+# bounded CPU sample of the Adobe workload: same x4 ratio and 7 timestamps on a 45x80 -> 180x320 crop
+CPU_SAMPLE = (45, 80, 180, 320, [k / 8 for k in range(1, 8)])
+CPU_SAMPLE_NOTE = "Adobe240 workload cropped to LR 45x80 -> 180x320, all 7 timestamps (1/16 of the pixels), fp32, torch CPU"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="motif", choices=["motif", "reference"])
+    ap.add_argument("--workload", default="adobe240_x4_t8")
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from motif_b200 import synthetic
+
+    H, W, HH, WW, times = synthetic.WORKLOADS[args.workload]
+    B, N = 1, len(times)
+    qs = HH * WW
+    config = {"workload": f"{args.workload}: LR {H}x{W} -> HR {HH}x{WW}, {N} timestamps, B=1, synthetic latents + synthetic best.pth-layout weights",
+              "l2": "per-step working set (imnet features 472 MB + splat accumulators 491 MB) >> 126 MB L2; no explicit flush",
+              "parallelism": f"timestamps sharded over {world} rank(s), NCCL broadcast of LR latents per step" if world > 1 else "single GPU"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(CPU_SAMPLE, max(1, min(args.steps, 3)), min(args.warmup, 1), CPU_SAMPLE_NOTE)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+
+    from motif_b200 import _lib, sharding
+    from motif_b200.decoder import SpaceTimeDecoder
+    from motif_b200.softsplat_cp import FunctionSoftsplat
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    params = synthetic.synthetic_params(seed=0)
+    dec = SpaceTimeDecoder(params, device=dev, precision=args.precision)
+    feat_h, ff_h, res_h = [t.pin_memory() for t in synthetic.synthetic_latents(B, H, W, seed=0)]
+    if rank == 0:
+        feat, ff, res = feat_h.to(dev), ff_h.to(dev), res_h.to(dev)
+    else:
+        feat, ff, res = [torch.empty_like(t, device=dev) for t in (feat_h, ff_h, res_h)]
+    tt = torch.tensor([times])
+    ranges = sharding.partition_timestamps(N, world)
+    n0, n1 = ranges[rank]
+    out_h = torch.empty(max(n1 - n0, 1), B, 3, HH, WW, dtype=torch.float32).pin_memory()
+
+    def step(from_host: bool):
+        nonlocal feat, ff, res
+        if from_host and rank == 0:
+            feat.copy_(feat_h, non_blocking=True)
+            ff.copy_(ff_h, non_blocking=True)
+            res.copy_(res_h, non_blocking=True)
+        if world > 1:
+            f2, g2, r2 = sharding.broadcast_latents(feat, ff, res, src=0)
+        else:
+            f2, g2, r2 = feat, ff, res
+        rgb, _ = dec.decode(f2, g2, r2, tt, (HH, WW), n_range=(n0, n1), return_flow=False)
+        if from_host and n1 > n0:
+            out_h[: n1 - n0].copy_(rgb[n0:n1], non_blocking=True)
+        return rgb
+
+    def timed(from_host: bool, steps: int, profile: bool):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            _lib.prof_enable(True)
+        lib.motif_reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = lib.motif_launch_count()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+            dist.barrier()
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernel_names = ["imnet_kernel", "flow_splat_kernel", "synth_kernel", "imnet_tc_kernel", "flow_splat_tc_kernel", "synth_tc_kernel"]
+    ms, launches = timed(False, args.steps, profile=True)
+    prof = _lib.prof_collect(kernel_names)
+    _lib.prof_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    step(True)
+    torch.cuda.synchronize()
+    ms_e2e, _ = timed(True, args.steps, profile=False)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    units_per_step = N * qs
+    value = units_per_step * args.steps / (ms * 1e-3)
+    e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = (feat_h.numel() + ff_h.numel() + res_h.numel()) * 4
+    d2h = N * B * 3 * qs * 4
+
+    # ---- roofline of the dominant kernel of the step (per launch, CUDA events on the launch stream) ----
+    flops_per_launch = {
+        "imnet_kernel": FLOP_IMNET_ROW * 2 * B * qs, "imnet_tc_kernel": FLOP_IMNET_ROW * 2 * B * qs,
+        "flow_splat_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "flow_splat_tc_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs,
+        "synth_kernel": FLOP_SYNTH_ROW * qs, "synth_tc_kernel": FLOP_SYNTH_ROW * qs,
+    }
+    live = {k: v for k, v in prof.items() if v[1] > 0}
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    kernels = {}
+    for k, (tot_ms, cnt) in live.items():
+        avg = tot_ms / cnt
+        kernels[k] = {"launches_per_step": cnt / args.steps, "avg_ms": avg, "share_of_step": tot_ms / ms,
+                      "tflops": flops_per_launch[k] / (avg * 1e-3) / 1e12}
+    roofline = None
+    if live:
+        dom = max(live, key=lambda k: live[k][0])
+        a = kernels[dom]["tflops"]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": a, "peak": tf32_peak, "unit": "TFLOP/s", "frac": a / tf32_peak, "traffic": None,
+                    "peak_note": f"TF32 dense = 0.5 x bf16 sustained, {peaks['source']}; algorithmic FLOPs (K un-padded, one pass counted)"}
+
+    # ---- HBM roofline of the stand-alone softmax splat operator (C=130, one 720x1280 reference frame) ----
+    torch.manual_seed(0)
+    x = torch.randn(1, 130, HH, WW, device=dev)
+    low = torch.randn(1, 2, HH // 16, WW // 16, device=dev) * 6
+    fl = torch.nn.functional.interpolate(low, size=(HH, WW), mode="bilinear", align_corners=False).contiguous()
+    z = -torch.rand(1, 1, HH, WW, device=dev)
+    for _ in range(3):
+        FunctionSoftsplat(x, fl, z, "softmax")
+    torch.cuda.synchronize()
+    _lib.prof_enable(True)
+    reps = 10
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(reps):
+        FunctionSoftsplat(x, fl, z, "softmax")
+    s1.record()
+    torch.cuda.synchronize()
+    sp = _lib.prof_collect(["splat_bin_kernel", "splat_gather_kernel", "splat_scatter_kernel"])
+    _lib.prof_enable(False)
+    op_ms = s0.elapsed_time(s1) / reps
+    gather_ms = sp["splat_gather_kernel"][0] / max(sp["splat_gather_kernel"][1], 1)
+    alg_bytes = SPLAT_BYTES_PER_SRC * qs
+    roofline_splat = {"kernel": "splat_gather_kernel", "bound": "hbm", "achieved": alg_bytes / (gather_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                      "frac": alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                      "operator_gbs": alg_bytes / (op_ms * 1e-3) / 1e9, "operator_ms": op_ms,
+                      "bin_ms": sp["splat_bin_kernel"][0] / max(sp["splat_bin_kernel"][1], 1),
+                      "note": f"FunctionSoftsplat softmax, [1,130,{HH},{WW}], 1056 B per source pixel; {peaks['source']}"}
+    del x, fl, z
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(CPU_SAMPLE, 2, 1, CPU_SAMPLE_NOTE)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "tf32x3 (fp32-equivalent)" if args.precision == "tf32x3" else "f32", "data": "synthetic", "config": config,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline, "roofline_splat": roofline_splat, "kernels": kernels,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

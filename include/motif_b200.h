@@ -1,0 +1,156 @@
+/*
+ * motif_b200 -- C ABI of the Blackwell (sm_100a) implementation of MoTIF's per-pixel
+ * inference hot path.  Plain pointers and sizes only; no torch types.  Every pointer is
+ * a DEVICE pointer to fp32 (or int32 where stated), contiguous in the layout named.
+ * `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success, a
+ * positive cudaError_t on a CUDA failure or a negative MOTIF_E_* code on a bad argument;
+ * motif_last_error() gives the message (thread-local).  Kernels never allocate: scratch
+ * comes from the caller (`workspace`).  Functions are re-entrant and launch only on the
+ * stream they are given (the reference launches on torch.cuda.current_stream(),
+ * models/softsplat_cp.py:248).
+ *
+ * The reference has no native ABI: its operators are CUDA-C strings compiled by cupy and
+ * launched as  cupy.RawModule(...).get_function(name)(grid, block, args, stream)
+ * (models/softsplat_cp.py:215-249, OpticalFlow/correlation.py:286-341).  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference).
+ */
+#ifndef MOTIF_B200_H_
+#define MOTIF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOTIF_ABI_VERSION 1
+
+#define MOTIF_E_BADARG (-1)   /* null pointer, non-positive size, unknown mode        */
+#define MOTIF_E_WORKSPACE (-2) /* workspace smaller than the *_workspace_bytes() answer */
+#define MOTIF_E_UNSUPPORTED (-3)
+
+int motif_abi_version(void);
+const char* motif_last_error(void);
+/* Number of kernels this library launched since the last motif_reset_launch_count()
+ * (process-wide; used by bench.py for its `gpu_launches` claim). */
+long long motif_launch_count(void);
+void motif_reset_launch_count(void);
+/* Optional per-kernel timing: when enabled, the library brackets each of its main kernels with
+ * CUDA events on the launch stream.  motif_prof_collect() synchronises the device and sums the
+ * recorded durations (ms) and launch counts for the kernel names given; returns the number of
+ * recorded launches and clears the record. */
+void motif_prof_enable(int on);
+int motif_prof_collect(const char* const* names, int n_names, double* out_ms, long long* out_count);
+
+/* ------------------------------------------------------------------------------------
+ * Forward splatting.  Replaces kernel_Softsplat_updateOutput + FunctionSoftsplat of
+ * models/softsplat_cp.py:12-52, 221-259, 320-347.
+ *   in     [n, c, h, w]      flow [n, 2, h, w] (ch0 = x, ch1 = y, destination pixels)
+ *   metric [n, 1, h, w]      (LINEAR / SOFTMAX; NULL otherwise)
+ *   out    [n, c_out, h, w]  c_out = c for SUMMATION, c + 1 otherwise; the last channel is
+ *                            the normaliser (ones / metric / exp(metric) splatted).  The
+ *                            output is UN-normalised, as in the reference (:336-346).
+ * `out` needs no initialisation.  Non-finite flow: the source pixel is skipped (the
+ * reference traps on a device assert, :25-26).
+ * motif_splat_fwd is the destination-centric production kernel (deterministic, no float
+ * atomics on the common path); it needs motif_splat_workspace_bytes(n, h, w) bytes.
+ * motif_splat_fwd_atomic is the reference-order float-atomic scatter, kept as the overflow
+ * path of the former and as an on-device cross-check.
+ * ---------------------------------------------------------------------------------- */
+enum { MOTIF_SPLAT_SUMMATION = 0, MOTIF_SPLAT_AVERAGE = 1, MOTIF_SPLAT_LINEAR = 2, MOTIF_SPLAT_SOFTMAX = 3 };
+
+size_t motif_splat_workspace_bytes(int n, int h, int w);
+int motif_splat_fwd(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w,
+                    int mode, void* workspace, size_t workspace_bytes, void* stream);
+int motif_splat_fwd_atomic(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h,
+                           int w, int mode, void* stream);
+
+/* Max splat: out = max(1.0, max over contributions of in*weight).  Replaces
+ * models/softsplat_max_cp.py:12-58, 240-278 (output initialised to ONES, :254).
+ *   in [n,c,h,w], flow [n,2,h,w], out [n,c,h,w] (needs no initialisation). */
+int motif_splat_max_fwd(const float* in, const float* flow, float* out, int n, int c, int h, int w, void* stream);
+
+/* Count splat: number of source pixels whose 2x2 footprint covers each destination pixel.
+ * Replaces models/softsplat_count_cp.py:14-52, 117-165 (the wrapper feeds ones; the input
+ * values are ignored).   flow [n,2,h,w], out [n,1,h,w] fp32 holding integers. */
+int motif_splat_count_fwd(const float* flow, float* out, int n, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * PWC-Net cost volume.  Replaces kernel_Correlation_rearrange + kernel_Correlation_updateOutput
+ * + _FunctionCorrelation.forward of OpticalFlow/correlation.py:17-112, 294-348.
+ *   first, second [b, c, h, w]   out [b, 81, h, w]
+ *   out[b, 9*(dy+4)+(dx+4), y, x] = (1/c) * sum_k first[b,k,y,x] * second[b,k,y+dy,x+dx], zero outside.
+ * ---------------------------------------------------------------------------------- */
+int motif_corr_fwd(const float* first, const float* second, float* out, int b, int c, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Space-time local implicit decoder.  Replaces models/modules/Ours.py:659-858 (LunaTokis.forward
+ * from make_coord to the clamp) with SIREN MLPs of models/modules/SIREN.py:44-45, 76-79.
+ * ---------------------------------------------------------------------------------- */
+
+/* One SIREN MLP in the checkpoint (state_dict) layout: weight[l] is [out_l, in_l] row-major,
+ * bias[l] is [out_l]; layers 0..n_layers-2 are sine layers (omega = 30), the last is linear. */
+typedef struct {
+  int n_layers;
+  const float* weight[5];
+  const float* bias[5];
+} motif_siren_t;
+
+typedef struct {
+  int B;      /* clips                                  */
+  int N;      /* target timestamps per clip             */
+  int H, W;   /* LR latent size                         */
+  int HH, WW; /* HR output size                         */
+  /* 1-D coordinate sequences exactly as make_coord (Ours.py:874-889) builds them on the
+   * host in fp32: seq[i] = fl(fl(-1 + 1/n) + fl(fl(2/n) * i)).  Device pointers. */
+  const float* seq_hh; /* [HH] */
+  const float* seq_ww; /* [WW] */
+  const float* seq_h;  /* [H]  */
+  const float* seq_w;  /* [W]  */
+  float flow_scale;    /* fl32(HH / H), the python-double ratio of Ours.py:794 cast to fp32 */
+} motif_geom_t;
+
+/* Nearest-latent index and relative coordinate of every HR query (Ours.py:667-689, 704,
+ * 720-722; ATen grid_sample nearest, align_corners=False).  For bit-exactness tests.
+ *   iy, ix [HH*WW] int32; coord [HH*WW, 2] shifted+clamped (y,x); rel [HH*WW, 2] (y,x). */
+int motif_query_geometry(const motif_geom_t* g, int32_t* iy, int32_t* ix, float* coord, float* rel, void* stream);
+
+/* LR latents NCHW -> pixel-major ("channel-last") [rows, H*W, 64]; rows = leading dim. */
+int motif_pack_latents(const float* nchw, float* packed, int rows, int channels, int hw, void* stream);
+
+typedef struct {
+  motif_geom_t geom;
+  /* pixel-major LR latents (motif_pack_latents) */
+  const float* feat;      /* [2B, H*W, 64]  F_0^L, F_1^L  leading index r*B+b (Ours.py:609)  */
+  const float* flow_feat; /* [2B, H*W, 64]  T_0^L, T_1^L  (Ours.py:638)                    */
+  const float* residual;  /* [B,  H*W, 64]  F_01^L        (Ours.py:607)                    */
+  const float* target_t;  /* [B, N] HOST pointer                                            */
+  motif_siren_t imnet, flow_imnet, synth_net;
+  float alpha;            /* LunaTokis.alpha (Ours.py:509)                                  */
+  /* outputs */
+  float* rgb;      /* [N, B, 3, HH, WW] clamped to [0,1] (Ours.py:858)                      */
+  float* flow_out; /* [2*B*N, 2, HH, WW] = flow_hr / 20 / (HH/H) (Ours.py:858); may be NULL  */
+  /* scratch: motif_decode_workspace_bytes() bytes */
+  void* workspace;
+  size_t workspace_bytes;
+  /* optional debug taps (may be NULL), NCHW like the reference tensors:
+   *   dbg_splat [B*N, 133, HH, WW] = blended splat (130) + extra (3)  (Ours.py:810-836) */
+  float* dbg_synth_in; /* [B*N, 198, HH, WW] the synth_net input (Ours.py:839-844) */
+  int n_begin, n_end;  /* timestamps [n_begin, n_end) of each clip are decoded (sharding) */
+  int precision;       /* MOTIF_PRECISION_*: arithmetic of the three SIREN MLPs               */
+} motif_decode_t;
+
+/* MLP arithmetic.  TF32X3: tcgen05 tensor cores, error-compensated 3xTF32 (fp32-equivalent
+ * products, fp32 TMEM accumulation).  FP32: CUDA-core FFMA + sinf, the numerical yardstick. */
+enum { MOTIF_PRECISION_TF32X3 = 0, MOTIF_PRECISION_FP32 = 1 };
+
+size_t motif_decode_workspace_bytes(int B, int N, int H, int W, int HH, int WW);
+/* Whole hot path for one batch of clips from resident LR latents: imnet once per clip, then
+ * per timestamp flow_imnet -> 3 splats of both references -> blend -> synth_net -> clamp. */
+int motif_decode(const motif_decode_t* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTIF_B200_H_ */

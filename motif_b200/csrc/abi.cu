@@ -1,0 +1,81 @@
+// Error reporting, launch accounting and the decode entry point of libmotif_b200.
+#include <stdarg.h>
+#include <string.h>
+
+#include "decoder_common.cuh"
+
+namespace motif {
+
+thread_local char g_last_error[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+// ---- per-kernel event timing ----------------------------------------------------------------------
+constexpr int kProfMax = 8192;
+static bool g_prof_on = false;
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_ev[kProfMax][2];
+static const char* g_prof_name[kProfMax];
+static bool g_prof_created[kProfMax];
+
+ProfScope::ProfScope(const char* name, cudaStream_t stream) : slot(-1), st(stream) {
+  if (!g_prof_on || g_prof_n >= kProfMax) return;
+  slot = g_prof_n++;
+  if (!g_prof_created[slot]) {
+    cudaEventCreate(&g_prof_ev[slot][0]);
+    cudaEventCreate(&g_prof_ev[slot][1]);
+    g_prof_created[slot] = true;
+  }
+  g_prof_name[slot] = name;
+  cudaEventRecord(g_prof_ev[slot][0], st);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof_ev[slot][1], st);
+}
+
+}  // namespace motif
+
+using namespace motif;
+
+extern "C" void motif_prof_enable(int on) {
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+}
+
+// Synchronises the device, then sums the recorded intervals per kernel name into `out_ms` / `out_count`
+// for the names given (exact string match).  Returns the number of recorded launches.
+extern "C" int motif_prof_collect(const char* const* names, int n_names, double* out_ms, long long* out_count) {
+  cudaDeviceSynchronize();
+  for (int i = 0; i < n_names; ++i) {
+    out_ms[i] = 0.0;
+    out_count[i] = 0;
+  }
+  for (int s = 0; s < g_prof_n; ++s) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_ev[s][0], g_prof_ev[s][1]) != cudaSuccess) continue;
+    for (int i = 0; i < n_names; ++i)
+      if (strcmp(names[i], g_prof_name[s]) == 0) {
+        out_ms[i] += ms;
+        out_count[i] += 1;
+      }
+  }
+  const int n = g_prof_n;
+  g_prof_n = 0;
+  return n;
+}
+
+extern "C" int motif_abi_version(void) { return MOTIF_ABI_VERSION; }
+extern "C" const char* motif_last_error(void) { return g_last_error; }
+extern "C" long long motif_launch_count(void) { return g_launches.load(); }
+extern "C" void motif_reset_launch_count(void) { g_launches.store(0); }
+
+extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
+  return decode_simt(args, (cudaStream_t)stream);
+}

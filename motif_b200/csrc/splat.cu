@@ -1,0 +1,389 @@
+// Forward splatting for sm_100a: FunctionSoftsplat (summation/average/linear/softmax) plus the max and
+// count reliability variants.  Semantics: models/softsplat_cp.py:12-52, 320-347;
+// softsplat_max_cp.py:12-58, 254; softsplat_count_cp.py:14-52, 163-165 (reference paths).
+//
+// Two algorithms for the sum splat:
+//  * destination-centric ("bin then gather"): a first pass bins, per destination pixel, the (source,
+//    weight) pairs whose 2x2 footprint covers it (int atomics only, one pass over the flow, amortised
+//    over all C channels); a second pass has one thread per DESTINATION pixel accumulate its <= K
+//    contributions for every channel with coalesced reads of the NCHW planes and one coalesced store.
+//    No float atomics, output written exactly once, deterministic: contributions are added in source
+//    raster order, which is the order a single thread executing the reference kernel adds them.
+//    Destinations with more than K contributions get the surplus through the atomic kernel below.
+//  * reference-order scatter with red.global.add.f32: the reference algorithm with the flow/weights
+//    hoisted out of the channel loop; used for the overflow and as an on-device cross-check.
+#include "common.cuh"
+
+namespace motif {
+
+constexpr int kBinSlots = 8;  // contributions kept per destination pixel before overflowing
+
+struct SplatWorkspace {
+  int* count;      // [n*hw]   contributions per destination pixel
+  int* ent_src;    // [K][n*hw] source pixel (y*w+x) of slot k
+  float* ent_w;    // [K][n*hw] bilinear weight of slot k
+  unsigned char* ovf_mask;  // [n*hw] per SOURCE pixel: bit c set = corner c did not get a slot
+  int* ovf_total;  // [1]
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static size_t workspace_layout(int n, int h, int w, SplatWorkspace* ws, char* base) {
+  const size_t p = (size_t)n * h * w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* ptr = base ? base + off : nullptr;
+    off += align256(bytes);
+    return ptr;
+  };
+  char* a = take(p * sizeof(int));
+  char* b = take(p * sizeof(int) * kBinSlots);
+  char* c = take(p * sizeof(float) * kBinSlots);
+  char* d = take(p);
+  char* e = take(256);
+  if (ws) {
+    ws->count = (int*)a;
+    ws->ent_src = (int*)b;
+    ws->ent_w = (float*)c;
+    ws->ovf_mask = (unsigned char*)d;
+    ws->ovf_total = (int*)e;
+  }
+  return off;
+}
+
+template <int MODE>
+__device__ __forceinline__ float metric_scale(const float* metric, size_t idx) {
+  if (MODE == MOTIF_SPLAT_LINEAR) return metric[idx];
+  if (MODE == MOTIF_SPLAT_SOFTMAX) return expf(metric[idx]);
+  return 1.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference-order scatter.  One thread per source pixel, channel loop inside.
+// only_overflow: contribute only the corners flagged in ovf_mask (surplus of the binning pass).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                            const float* __restrict__ metric, float* __restrict__ out,
+                                                            int n, int c, int h, int w,
+                                                            const unsigned char* __restrict__ ovf_mask,
+                                                            const int* __restrict__ ovf_total) {
+  if (ovf_total != nullptr && *ovf_total == 0) return;
+  const int hw = h * w;
+  const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)n * hw;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(p / hw), s = (int)(p % hw);
+    unsigned mask = 0xF;
+    if (ovf_mask != nullptr) {
+      mask = ovf_mask[p];
+      if (mask == 0) continue;
+    }
+    const int y = s / w, x = s % w;
+    const Footprint f = footprint(x, y, flow[((size_t)b * 2 + 0) * hw + s], flow[((size_t)b * 2 + 1) * hw + s]);
+    if (!f.finite) continue;
+    int dst[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int cx, cy;
+      ok[k] = corner_inside(f, k, w, h, cx, cy) && ((mask >> k) & 1);
+      dst[k] = cy * w + cx;
+    }
+    if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+    const float m = metric_scale<MODE>(metric, p);
+    const float* src = in + (size_t)b * c * hw + s;
+    float* o = out + (size_t)b * c_out * hw;
+    for (int ch = 0; ch < c; ++ch) {
+      float v = src[(size_t)ch * hw];
+      if (MODE >= MOTIF_SPLAT_LINEAR) v = __fmul_rn(v, m);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) red_add_f32(o + (size_t)ch * hw + dst[k], __fmul_rn(v, f.w[k]));
+    }
+    if (MODE != MOTIF_SPLAT_SUMMATION) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) red_add_f32(o + (size_t)c * hw + dst[k], __fmul_rn(m, f.w[k]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Destination-centric pass 1: bin (source, weight) per destination pixel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) splat_bin_kernel(const float* __restrict__ flow, SplatWorkspace ws, int n, int h, int w) {
+  const int hw = h * w;
+  const size_t total = (size_t)n * hw;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(p / hw), s = (int)(p % hw);
+    const int y = s / w, x = s % w;
+    const Footprint f = footprint(x, y, flow[((size_t)b * 2 + 0) * hw + s], flow[((size_t)b * 2 + 1) * hw + s]);
+    if (!f.finite) continue;
+    unsigned overflow = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int cx, cy;
+      if (!corner_inside(f, k, w, h, cx, cy)) continue;
+      const size_t d = (size_t)b * hw + (size_t)cy * w + cx;
+      const int slot = atomicAdd(ws.count + d, 1);
+      if (slot < kBinSlots) {
+        ws.ent_src[(size_t)slot * total + d] = s;
+        ws.ent_w[(size_t)slot * total + d] = f.w[k];
+      } else {
+        overflow |= 1u << k;
+      }
+    }
+    if (overflow) {
+      ws.ovf_mask[p] = (unsigned char)overflow;
+      atomicAdd(ws.ovf_total, 1);
+    }
+  }
+}
+
+__device__ __forceinline__ void cswap(int& sa, float& wa, int& sb, float& wb) {
+  const bool sw = sa > sb;
+  const int ts = sw ? sb : sa;
+  const float tw = sw ? wb : wa;
+  sb = sw ? sa : sb;
+  wb = sw ? wa : wb;
+  sa = ts;
+  wa = tw;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Destination-centric pass 2: one thread per destination pixel, all channels.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metric,
+                                                           float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
+  const int hw = h * w;
+  const size_t total = (size_t)n * hw;
+  const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= hw) return;
+  const size_t gd = (size_t)b * hw + d;
+  const int cnt = min(ws.count[gd], kBinSlots);
+  int src[kBinSlots];
+  float wt[kBinSlots];
+#pragma unroll
+  for (int k = 0; k < kBinSlots; ++k) {
+    const bool live = k < cnt;
+    src[k] = live ? ws.ent_src[(size_t)k * total + gd] : 0x7fffffff;
+    wt[k] = live ? ws.ent_w[(size_t)k * total + gd] : 0.0f;
+  }
+  // sort by source index (Batcher odd-even merge network for 8 keys): the accumulation order becomes
+  // source raster order whatever order the binning atomics handed the slots out in.
+#define CS(a, b) cswap(src[a], wt[a], src[b], wt[b])
+  CS(0, 1); CS(2, 3); CS(4, 5); CS(6, 7);
+  CS(0, 2); CS(1, 3); CS(4, 6); CS(5, 7);
+  CS(1, 2); CS(5, 6);
+  CS(0, 4); CS(1, 5); CS(2, 6); CS(3, 7);
+  CS(2, 4); CS(3, 5);
+  CS(1, 2); CS(3, 4); CS(5, 6);
+#undef CS
+  float m[kBinSlots];
+#pragma unroll
+  for (int k = 0; k < kBinSlots; ++k) {
+    m[k] = 1.0f;
+    if (MODE >= MOTIF_SPLAT_LINEAR && k < cnt) m[k] = metric_scale<MODE>(metric, (size_t)b * hw + src[k]);
+    if (k >= cnt) src[k] = 0;
+  }
+  const float* ib = in + (size_t)b * c * hw;
+  float* ob = out + (size_t)b * c_out * hw + d;
+#pragma unroll 2
+  for (int ch = 0; ch < c; ++ch) {
+    const float* plane = ib + (size_t)ch * hw;
+    float v[kBinSlots];
+#pragma unroll
+    for (int k = 0; k < kBinSlots; ++k) v[k] = (k < cnt) ? __ldg(plane + src[k]) : 0.0f;
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kBinSlots; ++k) {
+      if (k < cnt) {
+        float t = v[k];
+        if (MODE >= MOTIF_SPLAT_LINEAR) t = __fmul_rn(t, m[k]);
+        acc = __fadd_rn(acc, __fmul_rn(t, wt[k]));
+      }
+    }
+    ob[(size_t)ch * hw] = acc;
+  }
+  if (MODE != MOTIF_SPLAT_SUMMATION) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kBinSlots; ++k)
+      if (k < cnt) acc = __fadd_rn(acc, __fmul_rn(m[k], wt[k]));
+    ob[(size_t)c * hw] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Max and count variants (single-channel in the shipped pipeline): reference-order atomics.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ p, float v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void __launch_bounds__(256) splat_max_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                        float* __restrict__ out, int n, int c, int h, int w) {
+  const int hw = h * w;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)n * hw;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(p / hw), s = (int)(p % hw);
+    const Footprint f = footprint(s % w, s / w, flow[((size_t)b * 2 + 0) * hw + s], flow[((size_t)b * 2 + 1) * hw + s]);
+    if (!f.finite) continue;
+    for (int ch = 0; ch < c; ++ch) {
+      const float v = in[((size_t)b * c + ch) * hw + s];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int cx, cy;
+        if (!corner_inside(f, k, w, h, cx, cy)) continue;
+        const float cand = __fmul_rn(v, f.w[k]);
+        // atomicMaxFloat (softsplat_max_cp.py:13-18) on a cell that starts at 1.0: only a candidate
+        // that is >= 0 can win (int compare); negative or NaN candidates never change the cell.
+        if (cand >= 0.0f) red_max_nonneg(out + ((size_t)b * c + ch) * hw + (size_t)cy * w + cx, cand);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) splat_count_kernel(const float* __restrict__ flow, float* __restrict__ out, int n, int h, int w) {
+  const int hw = h * w;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)n * hw;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(p / hw), s = (int)(p % hw);
+    // the reference count kernel has no isfinite assert; a non-finite position is out of the image anyway
+    const Footprint f = footprint(s % w, s / w, flow[((size_t)b * 2 + 0) * hw + s], flow[((size_t)b * 2 + 1) * hw + s]);
+    if (!f.finite) continue;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int cx, cy;
+      if (corner_inside(f, k, w, h, cx, cy)) red_add_f32(out + (size_t)b * hw + (size_t)cy * w + cx, 1.0f);
+    }
+  }
+}
+
+static int grid_for(long long work, int block) {
+  long long g = (work + block - 1) / block;
+  const long long cap = 148LL * 16;  // 148 SMs x resident CTAs; kernels are grid-stride
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+template <int MODE>
+static int launch_scatter(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w,
+                          const unsigned char* mask, const int* total, cudaStream_t st) {
+  {
+    ProfScope prof("splat_scatter_kernel", st);
+    splat_scatter_kernel<MODE><<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, metric, out, n, c, h, w, mask, total);
+    MOTIF_LAUNCHED("splat_scatter_kernel");
+  }
+  return 0;
+}
+
+template <int MODE>
+static int launch_gather(const float* in, const float* metric, float* out, const SplatWorkspace& ws, int n, int c, int h, int w,
+                         cudaStream_t st) {
+  dim3 grid(ceil_div((long long)h * w, 256), n);
+  {
+    ProfScope prof("splat_gather_kernel", st);
+    splat_gather_kernel<MODE><<<grid, 256, 0, st>>>(in, metric, out, ws, n, c, h, w);
+    MOTIF_LAUNCHED("splat_gather_kernel");
+  }
+  return 0;
+}
+
+static int check_splat_args(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w, int mode) {
+  MOTIF_REQUIRE(in && flow && out, "splat: null pointer");
+  MOTIF_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, "splat: non-positive size n=%d c=%d h=%d w=%d", n, c, h, w);
+  MOTIF_REQUIRE(mode >= MOTIF_SPLAT_SUMMATION && mode <= MOTIF_SPLAT_SOFTMAX, "splat: unknown mode %d", mode);
+  MOTIF_REQUIRE(mode < MOTIF_SPLAT_LINEAR || metric != nullptr, "splat: mode %d needs a metric", mode);
+  MOTIF_REQUIRE((long long)n * (c + 1) * h * w < (1LL << 40), "splat: tensor too large");
+  MOTIF_REQUIRE((long long)h * w < (1LL << 31), "splat: image too large");
+  return 0;
+}
+
+}  // namespace motif
+
+using namespace motif;
+
+extern "C" size_t motif_splat_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  return workspace_layout(n, h, w, nullptr, nullptr);
+}
+
+extern "C" int motif_splat_fwd_atomic(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h,
+                                      int w, int mode, void* stream) {
+  if (int rc = check_splat_args(in, flow, metric, out, n, c, h, w, mode)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int c_out = mode == MOTIF_SPLAT_SUMMATION ? c : c + 1;
+  MOTIF_CUDA(cudaMemsetAsync(out, 0, (size_t)n * c_out * h * w * sizeof(float), st));
+  switch (mode) {
+    case MOTIF_SPLAT_SUMMATION: return launch_scatter<MOTIF_SPLAT_SUMMATION>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
+    case MOTIF_SPLAT_AVERAGE: return launch_scatter<MOTIF_SPLAT_AVERAGE>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
+    case MOTIF_SPLAT_LINEAR: return launch_scatter<MOTIF_SPLAT_LINEAR>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
+    default: return launch_scatter<MOTIF_SPLAT_SOFTMAX>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
+  }
+}
+
+extern "C" int motif_splat_fwd(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w,
+                               int mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_splat_args(in, flow, metric, out, n, c, h, w, mode)) return rc;
+  MOTIF_REQUIRE(workspace != nullptr, "splat: null workspace");
+  if (workspace_bytes < motif_splat_workspace_bytes(n, h, w))
+    return fail(MOTIF_E_WORKSPACE, "splat: workspace %zu < %zu bytes", workspace_bytes, motif_splat_workspace_bytes(n, h, w));
+  cudaStream_t st = (cudaStream_t)stream;
+  SplatWorkspace ws;
+  workspace_layout(n, h, w, &ws, (char*)workspace);
+  const size_t p = (size_t)n * h * w;
+  MOTIF_CUDA(cudaMemsetAsync(ws.count, 0, p * sizeof(int), st));
+  MOTIF_CUDA(cudaMemsetAsync(ws.ovf_mask, 0, p, st));
+  MOTIF_CUDA(cudaMemsetAsync(ws.ovf_total, 0, sizeof(int), st));
+  {
+    ProfScope prof("splat_bin_kernel", st);
+    splat_bin_kernel<<<grid_for((long long)p, 256), 256, 0, st>>>(flow, ws, n, h, w);
+    MOTIF_LAUNCHED("splat_bin_kernel");
+  }
+  int rc;
+  switch (mode) {
+    case MOTIF_SPLAT_SUMMATION:
+      rc = launch_gather<MOTIF_SPLAT_SUMMATION>(in, metric, out, ws, n, c, h, w, st);
+      if (!rc) rc = launch_scatter<MOTIF_SPLAT_SUMMATION>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      break;
+    case MOTIF_SPLAT_AVERAGE:
+      rc = launch_gather<MOTIF_SPLAT_AVERAGE>(in, metric, out, ws, n, c, h, w, st);
+      if (!rc) rc = launch_scatter<MOTIF_SPLAT_AVERAGE>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      break;
+    case MOTIF_SPLAT_LINEAR:
+      rc = launch_gather<MOTIF_SPLAT_LINEAR>(in, metric, out, ws, n, c, h, w, st);
+      if (!rc) rc = launch_scatter<MOTIF_SPLAT_LINEAR>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      break;
+    default:
+      rc = launch_gather<MOTIF_SPLAT_SOFTMAX>(in, metric, out, ws, n, c, h, w, st);
+      if (!rc) rc = launch_scatter<MOTIF_SPLAT_SOFTMAX>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      break;
+  }
+  return rc;
+}
+
+extern "C" int motif_splat_max_fwd(const float* in, const float* flow, float* out, int n, int c, int h, int w, void* stream) {
+  if (int rc = check_splat_args(in, flow, nullptr, out, n, c, h, w, MOTIF_SPLAT_SUMMATION)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)n * c * h * w;
+  fill_kernel<<<grid_for((long long)total, 256), 256, 0, st>>>(out, 1.0f, total);
+  MOTIF_LAUNCHED("fill_kernel");
+  splat_max_kernel<<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, out, n, c, h, w);
+  MOTIF_LAUNCHED("splat_max_kernel");
+  return 0;
+}
+
+extern "C" int motif_splat_count_fwd(const float* flow, float* out, int n, int h, int w, void* stream) {
+  MOTIF_REQUIRE(flow && out, "splat_count: null pointer");
+  MOTIF_REQUIRE(n > 0 && h > 0 && w > 0, "splat_count: non-positive size");
+  cudaStream_t st = (cudaStream_t)stream;
+  MOTIF_CUDA(cudaMemsetAsync(out, 0, (size_t)n * h * w * sizeof(float), st));
+  splat_count_kernel<<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(flow, out, n, h, w);
+  MOTIF_LAUNCHED("splat_count_kernel");
+  return 0;
+}

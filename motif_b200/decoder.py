@@ -1,0 +1,203 @@
+"""Host mirror of the space-time local implicit decoder (reference ``models/modules/Ours.py:659-858``).
+
+``SpaceTimeDecoder`` owns the three SIREN MLPs' weights in the checkpoint (``state_dict``) layout
+of ``LunaTokis`` -- ``imnet.net.{0,1,2}.linear.{weight,bias}``, ``imnet.net.3.{weight,bias}``, the
+same for ``flow_imnet``, ``synth_net.net.{0..3}.linear.*``, ``synth_net.net.4.*`` and ``alpha``
+ -- and decodes HR frames from the resident LR latents with ONE call into
+``libmotif_b200.so`` (``motif_decode``): nearest-latent gather, ``imnet`` once per clip, then per
+timestamp ``flow_imnet`` -> three forward splats of both reference frames -> blend + reliability
+features -> ``synth_net`` -> clamp.
+
+The coordinate sequences are built on the host exactly as ``make_coord`` (``Ours.py:874-889``)
+builds them (fp32, two roundings per element) and only these 1-D tables are uploaded; the
+reference uploads the full ``[HH*WW, 2]`` meshgrid on every call (``Ours.py:667-668``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+HOT_PREFIXES = ("imnet.", "flow_imnet.", "synth_net.")
+_SIREN_LAYERS = {"imnet": 4, "flow_imnet": 4, "synth_net": 5}
+_SIREN_SHAPES = {
+    "flow_imnet": [(64, 67), (64, 64), (256, 64), (3, 256)],
+    "imnet": [(64, 66), (64, 64), (256, 64), (64, 256)],
+    "synth_net": [(64, 198), (64, 64), (64, 64), (256, 64), (3, 256)],
+}
+PRECISIONS = {"tf32x3": 0, "fp32": 1}
+
+
+def coord_sequence(n: int) -> torch.Tensor:
+    """1-D pixel-centre sequence of ``make_coord`` for an axis of length ``n`` (``Ours.py:874-889``):
+    python-double ``v0 + r`` and ``2 * r`` cast to fp32, one fp32 multiply, one fp32 add."""
+    r = (1 - (-1)) / (2 * n)
+    return -1 + r + (2 * r) * torch.arange(n).float()
+
+
+def hr_size_from_scale(H: int, W: int, scale) -> Tuple[int, int]:
+    """``Ours.py:525-529``: list form ``[[HH], [WW]]`` or ``round(H * scale)``."""
+    if isinstance(scale, list):
+        return int(scale[0][0]), int(scale[1][0])
+    return round(H * scale), round(W * scale)
+
+
+def _key(name: str, layer: int, last: bool, what: str) -> str:
+    return f"{name}.net.{layer}.{what}" if last else f"{name}.net.{layer}.linear.{what}"
+
+
+class SpaceTimeDecoder:
+    def __init__(self, params: Dict[str, torch.Tensor], device="cuda", precision: str = "tf32x3"):
+        _lib.load()  # fail loudly when the CUDA library is missing
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {list(PRECISIONS)}")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise NotImplementedError("SpaceTimeDecoder is CUDA-only")
+        self.precision = precision
+        self.params = {}
+        for name, n_layers in _SIREN_LAYERS.items():
+            for layer in range(n_layers):
+                last = layer == n_layers - 1
+                for what in ("weight", "bias"):
+                    k = _key(name, layer, last, what)
+                    if k not in params:
+                        raise KeyError(f"missing hot-path parameter {k!r}")
+                    t = params[k].detach().to(device=self.device, dtype=torch.float32).contiguous()
+                    want = _SIREN_SHAPES[name][layer] if what == "weight" else (_SIREN_SHAPES[name][layer][0],)
+                    if tuple(t.shape) != tuple(want):
+                        raise ValueError(f"{k}: expected shape {want}, got {tuple(t.shape)}")
+                    self.params[k] = t
+        if "alpha" not in params:
+            raise KeyError("missing hot-path parameter 'alpha'")
+        self.alpha = float(params["alpha"].detach().float().reshape(-1)[0].item())
+        self._seq_cache = {}
+        self._workspace = None
+
+    @classmethod
+    def from_state_dict(cls, state_dict, device="cuda", precision="tf32x3"):
+        """Accepts a full ``LunaTokis`` ``state_dict`` (e.g. ``best.pth``, optional ``module.`` prefix)."""
+        clean = {}
+        for k, v in state_dict.items():
+            k = k[7:] if k.startswith("module.") else k
+            if k == "alpha" or k.startswith(HOT_PREFIXES):
+                clean[k] = v
+        return cls(clean, device=device, precision=precision)
+
+    # ------------------------------------------------------------------------------------------
+    def _sequences(self, H, W, HH, WW):
+        key = (H, W, HH, WW)
+        if key not in self._seq_cache:
+            self._seq_cache[key] = tuple(coord_sequence(n).to(self.device) for n in (HH, WW, H, W))
+        return self._seq_cache[key]
+
+    def _geom(self, B, N, H, W, HH, WW):
+        s_hh, s_ww, s_h, s_w = self._sequences(H, W, HH, WW)
+        g = _lib.GeomT()
+        g.B, g.N, g.H, g.W, g.HH, g.WW = B, N, H, W, HH, WW
+        g.seq_hh, g.seq_ww, g.seq_h, g.seq_w = s_hh.data_ptr(), s_ww.data_ptr(), s_h.data_ptr(), s_w.data_ptr()
+        g.flow_scale = HH / H  # c_float rounds the python double to fp32, as torch does for a scalar operand
+        return g
+
+    def _siren(self, name):
+        s = _lib.SirenT()
+        n_layers = _SIREN_LAYERS[name]
+        s.n_layers = n_layers
+        for layer in range(n_layers):
+            last = layer == n_layers - 1
+            s.weight[layer] = self.params[_key(name, layer, last, "weight")].data_ptr()
+            s.bias[layer] = self.params[_key(name, layer, last, "bias")].data_ptr()
+        return s
+
+    def _get_workspace(self, nbytes):
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # ------------------------------------------------------------------------------------------
+    def query_geometry(self, H, W, HH, WW):
+        """Nearest-latent index map, shifted coordinates and relative coordinates of every HR query
+        (``Ours.py:667-689, 704, 720-722``).  Returns ``iy, ix`` int32 ``[HH*WW]``, ``coord``, ``rel`` ``[HH*WW, 2]``."""
+        lib = _lib.load()
+        g = self._geom(1, 1, H, W, HH, WW)
+        qs = HH * WW
+        iy = torch.empty(qs, dtype=torch.int32, device=self.device)
+        ix = torch.empty(qs, dtype=torch.int32, device=self.device)
+        coord = torch.empty(qs, 2, dtype=torch.float32, device=self.device)
+        rel = torch.empty(qs, 2, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = lib.motif_query_geometry(ctypes.byref(g), iy.data_ptr(), ix.data_ptr(), coord.data_ptr(), rel.data_ptr(),
+                                          _lib.current_stream_ptr(self.device))
+        _lib.check(rc, "motif_query_geometry")
+        return iy, ix, coord, rel
+
+    def pack_latents(self, x: torch.Tensor) -> torch.Tensor:
+        """NCHW ``[R, C, H, W]`` -> pixel-major ``[R, H*W, C]`` (device transpose kernel)."""
+        lib = _lib.load()
+        _lib.require_cuda_f32("latents", x, 4)
+        x = x.contiguous()
+        r, c, h, w = x.shape
+        out = torch.empty(r, h * w, c, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.motif_pack_latents(x.data_ptr(), out.data_ptr(), r, c, h * w, _lib.current_stream_ptr(x.device))
+        _lib.check(rc, "motif_pack_latents")
+        return out
+
+    def decode(
+        self,
+        feat: torch.Tensor,  # [2B, 64, H, W]  F_0^L, F_1^L (leading index r*B + b)
+        flow_feat: torch.Tensor,  # [2B, 64, H, W]  T_0^L, T_1^L
+        residual: torch.Tensor,  # [B, 64, H, W]   F_01^L
+        target_t,  # [B, N] tensor or nested sequence
+        hr_size: Tuple[int, int],
+        n_range: Optional[Tuple[int, int]] = None,
+        return_flow: bool = True,
+        debug_synth_in: bool = False,
+        precision: Optional[str] = None,
+    ):
+        """``Ours.py:659-858``.  Returns ``(rgb [N,B,3,HH,WW] in [0,1], flow_out [2BN,2,HH,WW] or None)``
+        (plus the ``[B*N,198,HH,WW]`` synth_net input when ``debug_synth_in``)."""
+        lib = _lib.load()
+        for nm, t in (("feat", feat), ("flow_feat", flow_feat), ("residual", residual)):
+            _lib.require_cuda_f32(nm, t, 4)
+        B = residual.shape[0]
+        H, W = residual.shape[-2:]
+        if feat.shape != (2 * B, 64, H, W) or flow_feat.shape != (2 * B, 64, H, W) or residual.shape[1] != 64:
+            raise ValueError(f"latent shapes do not match: feat {tuple(feat.shape)}, flow_feat {tuple(flow_feat.shape)}, residual {tuple(residual.shape)}")
+        HH, WW = int(hr_size[0]), int(hr_size[1])
+        tt = torch.as_tensor(target_t, dtype=torch.float32).detach().cpu().reshape(B, -1).contiguous() if not isinstance(target_t, torch.Tensor) \
+            else target_t.detach().to(device="cpu", dtype=torch.float32).reshape(B, -1).contiguous()
+        N = tt.shape[1]
+        n0, n1 = (0, N) if n_range is None else n_range
+        dev = self.device
+        with torch.cuda.device(dev):
+            featp = self.pack_latents(feat)
+            ffp = self.pack_latents(flow_feat)
+            resp = self.pack_latents(residual)
+            rgb = torch.empty(N, B, 3, HH, WW, dtype=torch.float32, device=dev)
+            flow_out = torch.empty(2 * B * N, 2, HH, WW, dtype=torch.float32, device=dev) if return_flow else None
+            dbg = torch.zeros(B * N, 198, HH, WW, dtype=torch.float32, device=dev) if debug_synth_in else None
+            nbytes = lib.motif_decode_workspace_bytes(B, N, H, W, HH, WW)
+            ws = self._get_workspace(nbytes)
+            a = _lib.DecodeT()
+            a.geom = self._geom(B, N, H, W, HH, WW)
+            a.feat, a.flow_feat, a.residual = featp.data_ptr(), ffp.data_ptr(), resp.data_ptr()
+            tt_arr = (ctypes.c_float * (B * N))(*tt.reshape(-1).tolist())
+            a.target_t = ctypes.cast(tt_arr, ctypes.POINTER(ctypes.c_float))
+            a.imnet, a.flow_imnet, a.synth_net = self._siren("imnet"), self._siren("flow_imnet"), self._siren("synth_net")
+            a.alpha = self.alpha
+            a.rgb = rgb.data_ptr()
+            a.flow_out = flow_out.data_ptr() if flow_out is not None else None
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+            a.dbg_synth_in = dbg.data_ptr() if dbg is not None else None
+            a.n_begin, a.n_end = int(n0), int(n1)
+            a.precision = PRECISIONS[precision or self.precision]
+            rc = lib.motif_decode(ctypes.byref(a), _lib.current_stream_ptr(dev))
+        _lib.check(rc, "motif_decode")
+        if debug_synth_in:
+            return rgb, flow_out, dbg
+        return rgb, flow_out

@@ -1,0 +1,137 @@
+"""GPU parity: the space-time local implicit decoder (Ours.py:659-858) through the C ABI."""
+import pytest
+import torch
+
+from conftest import hot_params, load_golden, psnr
+from oracle import decoder_ref
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3        # north_star: decoder outputs within 1e-3 max-abs ...
+PSNR_MIN = 60.0   # ... and 0.01 dB PSNR: PSNR(new, reference) >= 60 dB keeps any PSNR-vs-GT within 0.01 dB
+
+# (H, W, HH, WW): Vimeo x4, Adobe x4, x3.5 (round(H*3.5)), 4K x4, plus awkward ratios with index ties
+GEOMS = [(64, 112, 256, 448), (180, 320, 720, 1280), (180, 320, 630, 1120), (540, 960, 2160, 3840),
+         (16, 20, 56, 70), (7, 9, 20, 31), (5, 5, 5, 5), (12, 16, 18, 24), (3, 4, 96, 100)]
+
+
+def _decoder(params, precision):
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    return SpaceTimeDecoder(params, device="cuda", precision=precision)
+
+
+@pytest.mark.parametrize("geom", GEOMS)
+def test_query_geometry_bit_exact(geom):
+    """Nearest-latent index, shifted coordinate and relative coordinate: integer / bit equality."""
+    H, W, HH, WW = geom
+    dec = _decoder(decoder_ref.random_params(0), "fp32")
+    iy, ix, coord, rel = dec.query_geometry(H, W, HH, WW)
+    ref = decoder_ref.query_geometry(H, W, HH, WW)
+    assert torch.equal(iy.cpu().long(), ref["iy"])
+    assert torch.equal(ix.cpu().long(), ref["ix"])
+    assert torch.equal(coord.cpu(), ref["coord_"])
+    assert torch.equal(rel.cpu(), ref["rel"])
+
+
+def test_coord_sequence_host_matches_make_coord():
+    from motif_b200.decoder import coord_sequence
+
+    for n in (5, 56, 720, 1120, 3840):
+        assert torch.equal(coord_sequence(n), decoder_ref.make_coord((n,)).view(-1))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("case", ["decoder_raft", "decoder_x4", "decoder_x3p5_b2"])
+def test_decoder_vs_reference_golden(case, precision):
+    g = load_golden(case)
+    HH, WW = [int(v) for v in g["hr_size"]]
+    dec = _decoder(hot_params(g), precision)
+    rgb, flow = dec.decode(g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
+    assert rgb.shape == g["out"].shape and flow.shape == g["flow_out"].shape
+    d_rgb = (rgb.cpu() - g["out"]).abs().max().item()
+    d_flow = (flow.cpu() - g["flow_out"]).abs().max().item()
+    assert d_flow < 1e-5, d_flow           # raw flow units (pixels / (20 * scale))
+    assert d_rgb < TOL, d_rgb
+    assert psnr(rgb.cpu(), g["out"]) > PSNR_MIN
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_decoder_stages_vs_oracle(precision):
+    """Seeded O(1)-scaled weights; compares the blended splat + reliability features (the synth_net input,
+    Ours.py:839-844) and the final frames against the oracle."""
+    gen = torch.Generator().manual_seed(3)
+    B, N, H, W, HH, WW = 1, 2, 12, 20, 42, 70
+    feat = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    ff = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    res = torch.randn(B, 64, H, W, generator=gen) * 0.3
+    tt = torch.tensor([[0.25, 0.8]])
+    params = decoder_ref.random_params(seed=5, weight_gain=2.0, first_gain=12.0, alpha=-1.5, rgb_bias=0.5, rgb_gain=3.0)
+    r_rgb, r_flow, inter = decoder_ref.decode(feat, ff, res, tt, HH, WW, params, return_intermediates=True)
+    dec = _decoder(params, precision)
+    rgb, flow, synth_in = dec.decode(feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW), debug_synth_in=True)
+    assert (flow.cpu() - r_flow).abs().max().item() < 1e-5
+    d_in = (synth_in.cpu() - inter["synth_in"]).abs()
+    assert d_in[:, 130:133].max().item() < 1e-4      # zmax, count/16, wz/count
+    assert torch.equal(synth_in.cpu()[:, 131], inter["synth_in"][:, 131])  # count is exact
+    assert d_in.max().item() < TOL
+    assert (rgb.cpu() - r_rgb).abs().max().item() < TOL
+    assert psnr(rgb.cpu(), r_rgb) > PSNR_MIN
+
+
+def test_timestamp_range_equals_full_decode():
+    """Sharding contract: decoding timestamps [a,b) gives the same frames as the full decode."""
+    g = load_golden("decoder_x4")
+    HH, WW = [int(v) for v in g["hr_size"]]
+    dec = _decoder(hot_params(g), "tf32x3")
+    args = (g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
+    full, _ = dec.decode(*args)
+    part, _ = dec.decode(*args, n_range=(1, 3))
+    assert (part[1:3] - full[1:3]).abs().max().item() < 1e-5
+
+
+def test_vimeo_config_vs_oracle_and_psnr():
+    """BASELINE config 0 (64x112 -> 256x448, t=0.5): whole hot path against the oracle."""
+    gen = torch.Generator().manual_seed(11)
+    H, W, HH, WW = 64, 112, 256, 448
+    low = torch.randn(5, 64, H // 4, W // 4, generator=gen)
+    lat = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear") * 0.4
+    feat, ff, res = lat[0:2].contiguous(), lat[2:4].contiguous(), lat[4:5].contiguous()
+    tt = torch.tensor([[0.5]])
+    params = decoder_ref.random_params(seed=2, weight_gain=2.0, first_gain=10.0, alpha=-1.0, rgb_bias=0.5, rgb_gain=3.0)
+    r_rgb, r_flow = decoder_ref.decode(feat, ff, res, tt, HH, WW, params)
+    rgb, flow = _decoder(params, "tf32x3").decode(feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW))
+    assert (flow.cpu() - r_flow).abs().max().item() < 1e-5
+    assert (rgb.cpu() - r_rgb).abs().max().item() < TOL
+    assert psnr(rgb.cpu(), r_rgb) > PSNR_MIN
+
+
+def test_adobe_full_size_properties():
+    """BASELINE config 1 size (180x320 -> 720x1280, 7 timestamps): tf32x3 tensor path vs the exact-fp32
+    CUDA-core path on the device, finite and clamped output, determinism of shape/ordering."""
+    gen = torch.Generator().manual_seed(7)
+    H, W, HH, WW = 180, 320, 720, 1280
+    low = torch.randn(5, 64, H // 4, W // 4, generator=gen)
+    lat = torch.nn.functional.interpolate(low, size=(H, W), mode="bilinear") * 0.4
+    feat, ff, res = lat[0:2].contiguous().cuda(), lat[2:4].contiguous().cuda(), lat[4:5].contiguous().cuda()
+    tt = torch.tensor([[k / 8 for k in range(1, 8)]])
+    params = decoder_ref.random_params(seed=2, weight_gain=2.0, first_gain=10.0, alpha=-1.0, rgb_bias=0.5, rgb_gain=3.0)
+    a, fa = _decoder(params, "tf32x3").decode(feat, ff, res, tt, (HH, WW))
+    b, fb = _decoder(params, "fp32").decode(feat, ff, res, tt, (HH, WW), n_range=(0, 2))
+    assert a.shape == (7, 1, 3, HH, WW) and torch.isfinite(a).all()
+    assert a.min().item() >= 0.0 and a.max().item() <= 1.0
+    assert (fa[:2] - fb[:2]).abs().max().item() < 1e-5
+    assert (a[:2] - b[:2]).abs().max().item() < TOL
+    assert psnr(a[:2].cpu(), b[:2].cpu()) > PSNR_MIN
+
+
+def test_state_dict_loader_accepts_full_checkpoint_layout():
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    params = decoder_ref.random_params(0)
+    sd = {"module." + k: v for k, v in params.items()}
+    sd["module.encoder.dummy"] = torch.zeros(3)
+    dec = SpaceTimeDecoder.from_state_dict(sd, device="cuda")
+    assert dec.alpha == -20.0
+    with pytest.raises(KeyError):
+        SpaceTimeDecoder({k: v for k, v in params.items() if "synth_net.net.4" not in k})

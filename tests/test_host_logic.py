@@ -1,0 +1,79 @@
+"""CPU: host-side logic -- coordinate tables, HR size rule, timestamp sharding, and the world_size-2
+gloo run of the one exchange step of the path (latent broadcast) plus the frame gather."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from motif_b200 import sharding, synthetic
+from motif_b200.decoder import coord_sequence, hr_size_from_scale
+from oracle import decoder_ref
+
+
+def test_coord_sequence_is_make_coord():
+    for n in (1, 2, 5, 56, 70, 180, 630, 720, 1120, 1280, 2160, 3840):
+        assert torch.equal(coord_sequence(n), decoder_ref.make_coord((n,)).view(-1))
+
+
+def test_hr_size_rule():
+    assert hr_size_from_scale(180, 320, 4) == (720, 1280)
+    assert hr_size_from_scale(180, 320, 3.5) == (630, 1120)
+    assert hr_size_from_scale(16, 20, 3.5) == (56, 70)
+    assert hr_size_from_scale(64, 112, [[256], [448]]) == (256, 448)
+
+
+@pytest.mark.parametrize("n,world", [(7, 1), (7, 2), (7, 4), (7, 8), (11, 4), (1, 8), (3, 3)])
+def test_partition_covers_every_timestamp_once(n, world):
+    parts = sharding.partition_timestamps(n, world)
+    assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == n
+    covered = [i for b, e in parts for i in range(b, e)]
+    assert covered == list(range(n))
+    sizes = [e - b for b, e in parts]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_params_have_checkpoint_layout():
+    p = synthetic.synthetic_params(0)
+    ref = decoder_ref.random_params(0)
+    assert set(p) == set(ref)
+    assert all(p[k].shape == ref[k].shape for k in p)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_ts):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, H, W = 1, 6, 8
+        if rank == 0:
+            feat, ff, res = synthetic.synthetic_latents(B, H, W, seed=3)
+        else:
+            feat, ff, res = torch.zeros(2 * B, 64, H, W), torch.zeros(2 * B, 64, H, W), torch.zeros(B, 64, H, W)
+        feat, ff, res = sharding.broadcast_latents(feat, ff, res, src=0)
+        want = synthetic.synthetic_latents(B, H, W, seed=3)
+        assert torch.equal(feat, want[0]) and torch.equal(ff, want[1]) and torch.equal(res, want[2])
+        # every rank "decodes" its timestamps: frame n is filled with n, then frames are gathered
+        ranges = sharding.partition_timestamps(n_ts, world)
+        b, e = ranges[rank]
+        local = torch.stack([torch.full((B, 3, 4, 5), float(n)) for n in range(b, e)]) if e > b else torch.zeros(0, B, 3, 4, 5)
+        full = sharding.gather_frames(local, ranges)
+        assert full.shape == (n_ts, B, 3, 4, 5)
+        assert torch.equal(full[:, 0, 0, 0, 0], torch.arange(n_ts, dtype=torch.float32))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_ts", [7, 1])
+def test_two_rank_gloo_broadcast_and_gather(n_ts):
+    mp.spawn(_worker, args=(2, _free_port(), n_ts), nprocs=2, join=True)

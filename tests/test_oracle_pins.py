@@ -1,0 +1,79 @@
+"""CPU: the oracle restatements against the committed golden vectors (which were produced by the
+reference's own code, see oracle/make_golden.py) and, where the reference checkout is present,
+against the reference kernels compiled for the host (oracle/build_ref.py)."""
+import pytest
+import torch
+
+from conftest import hot_params, load_golden
+from oracle import build_ref, correlation_ref, decoder_ref, softsplat_ref
+
+SPLAT_CASES = ["splat_s05", "splat_s4", "splat_s32"]
+
+
+@pytest.mark.parametrize("case", SPLAT_CASES)
+def test_splat_oracle_matches_reference_kernels_bit_exact(case):
+    g = load_golden(case)
+    inp, flow, metric = g["input"], g["flow"], g["metric"]
+    assert torch.equal(softsplat_ref.splat_sum(inp, flow), g["out_summation"])
+    for mode in ("average", "linear", "softmax"):
+        out, norm = softsplat_ref.function_softsplat(inp, flow, metric, mode)
+        assert torch.equal(torch.cat([out, norm], 1), g["out_" + mode]), mode
+    assert torch.equal(softsplat_ref.function_softsplat_max(inp, flow), g["out_max"])
+    assert torch.equal(softsplat_ref.function_softsplat_max(metric.exp(), flow), g["out_max_exp"])
+    assert torch.equal(softsplat_ref.function_softsplat_count(inp, flow), g["out_count"])
+
+
+def test_splat_summation_contract():
+    g = load_golden("splat_s4")
+    out, norm = softsplat_ref.function_softsplat(g["input"], g["flow"], None, "summation")
+    assert norm is None and torch.equal(out, g["out_summation"])
+
+
+def test_max_splat_never_below_one_and_count_integer():
+    g = load_golden("splat_s32")
+    assert (g["out_max"] >= 1.0).all()
+    assert torch.equal(g["out_count"], g["out_count"].round())
+
+
+@pytest.mark.parametrize("case", ["correlation_c8", "correlation_c32", "correlation_c196"])
+def test_correlation_oracle(case):
+    g = load_golden(case)
+    out = correlation_ref.function_correlation(g["first"], g["second"])
+    assert out.shape == g["out"].shape
+    assert (out - g["out"]).abs().max().item() < 1e-5
+
+
+def test_correlation_lane_order_small():
+    g = load_golden("correlation_c8")
+    out = correlation_ref.function_correlation_lane_order(g["first"], g["second"])
+    assert (out - g["out"]).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("case", ["decoder_raft", "decoder_x4", "decoder_x3p5_b2"])
+def test_decoder_oracle_reproduces_reference_forward(case):
+    g = load_golden(case)
+    HH, WW = [int(v) for v in g["hr_size"]]
+    rgb, flow = decoder_ref.decode(g["feat"], g["flow_feat"], g["residual"], g["target_t"], HH, WW, hot_params(g))
+    assert rgb.shape == g["out"].shape and flow.shape == g["flow_out"].shape
+    # bit-exact on the machine that generated the vectors; other CPUs may pick other GEMM/sin kernels
+    assert (rgb - g["out"]).abs().max().item() < 2e-5
+    assert (flow - g["flow_out"]).abs().max().item() < 2e-5
+
+
+def test_hr_size_rounding_matches_reference_rule():
+    g = load_golden("decoder_x3p5_b2")
+    H, W = g["feat"].shape[-2:]
+    assert [int(v) for v in g["hr_size"]] == [round(H * 3.5), round(W * 3.5)]
+
+
+@pytest.mark.skipif(not build_ref.reference_available(), reason="reference checkout absent (GPU box)")
+def test_oracle_against_host_compiled_reference_kernels():
+    gen = torch.Generator().manual_seed(5)
+    inp = torch.randn(2, 4, 13, 19, generator=gen)
+    flow = torch.randn(2, 2, 13, 19, generator=gen) * 3
+    assert torch.equal(build_ref.ref_splat_sum(inp, flow), softsplat_ref.splat_sum(inp, flow))
+    assert torch.equal(build_ref.ref_splat_max(inp.exp(), flow), softsplat_ref.splat_max(inp.exp(), flow))
+    assert torch.equal(build_ref.ref_splat_count(torch.ones(2, 1, 13, 19), flow), softsplat_ref.function_softsplat_count(inp, flow))
+    f1 = torch.randn(1, 20, 7, 9, generator=gen)
+    f2 = torch.randn(1, 20, 7, 9, generator=gen)
+    assert (build_ref.ref_correlation(f1, f2) - correlation_ref.function_correlation(f1, f2)).abs().max().item() < 1e-6

@@ -1,0 +1,170 @@
+"""GPU parity: the three forward-splat operators through the C ABI against the oracle / golden vectors."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import softsplat_ref
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["splat_s05", "splat_s4", "splat_s32"]
+MODES = ["average", "linear", "softmax"]
+TOL = 1e-3  # north_star: splat outputs within 1e-3 max-abs (float atomics are order-dependent)
+
+
+def _cuda(g):
+    return {k: v.cuda() for k, v in g.items()}
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_sum_splat_destination_centric_is_bit_exact_vs_reference_raster_order(case):
+    """No destination in the golden cases has more than 8 contributions except in s32/s05 corners, where
+    the surplus goes through float atomics: compare exactly where count <= 8, with tolerance elsewhere."""
+    from motif_b200.softsplat_cp import FunctionSoftsplat
+
+    g = _cuda(load_golden(case))
+    few = (g["out_count"] <= 8)
+    out, norm = FunctionSoftsplat(g["input"], g["flow"], None, "summation")
+    assert norm is None
+    ref = g["out_summation"]
+    assert torch.equal(out[few.expand_as(out)], ref[few.expand_as(ref)])
+    assert (out - ref).abs().max().item() < TOL
+    for mode in MODES:
+        out, norm = FunctionSoftsplat(g["input"], g["flow"], g["metric"], mode)
+        full = torch.cat([out, norm], 1)
+        ref = g["out_" + mode]
+        assert full.shape == ref.shape
+        tol = 0.0 if mode != "softmax" else 2e-6  # device expf vs host exp may differ by an ulp
+        diff = (full - ref).abs()
+        assert diff[few.expand_as(diff)].max().item() <= tol * max(1.0, ref.abs().max().item()), mode
+        assert diff.max().item() < TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_atomic_scatter_variant(case):
+    from motif_b200.softsplat_cp import _splat
+
+    g = _cuda(load_golden(case))
+    for mode_name, mode in (("summation", 0), ("average", 1), ("linear", 2), ("softmax", 3)):
+        out = _splat(g["input"], g["flow"], g["metric"] if mode >= 2 else None, mode, atomic=True)
+        assert (out - g["out_" + mode_name]).abs().max().item() < TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_max_and_count_exact(case):
+    from motif_b200 import softsplat_count_cp, softsplat_max_cp
+
+    g = _cuda(load_golden(case))
+    assert torch.equal(softsplat_max_cp.FunctionSoftsplat(g["input"], g["flow"]), g["out_max"])
+    n, _, h, w = g["input"].shape
+    assert torch.equal(softsplat_max_cp.FunctionSoftsplat(g["metric"].exp().contiguous(), g["flow"]), g["out_max_exp"]) or \
+        (softsplat_max_cp.FunctionSoftsplat(g["metric"].exp().contiguous(), g["flow"]) - g["out_max_exp"]).abs().max().item() < 1e-6
+    cnt = softsplat_count_cp.FunctionSoftsplat(g["input"], g["flow"])
+    assert cnt.shape == (n, 1, h, w) and not cnt.requires_grad
+    assert torch.equal(cnt, g["out_count"])
+
+
+@pytest.mark.parametrize("sigma", [0.5, 4.0, 32.0])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_vs_oracle_seeded(sigma, seed):
+    from motif_b200 import softsplat_count_cp, softsplat_max_cp
+    from motif_b200.softsplat_cp import FunctionSoftsplat
+
+    gen = torch.Generator().manual_seed(seed)
+    n, c, h, w = 2, 7, 37, 53
+    inp = torch.randn(n, c, h, w, generator=gen)
+    flow = torch.randn(n, 2, h, w, generator=gen) * sigma
+    metric = -torch.randn(n, 1, h, w, generator=gen).abs() * 2
+    for mode in ["average", "linear", "softmax"]:
+        ro, rn = softsplat_ref.function_softsplat(inp, flow, metric, mode)
+        o, nn_ = FunctionSoftsplat(inp.cuda(), flow.cuda(), metric.cuda(), mode)
+        assert (o.cpu() - ro).abs().max().item() < TOL and (nn_.cpu() - rn).abs().max().item() < TOL
+    assert torch.equal(softsplat_max_cp.FunctionSoftsplat(inp.exp().cuda(), flow.cuda()).cpu(), softsplat_ref.function_softsplat_max(inp.exp(), flow))
+    assert torch.equal(softsplat_count_cp.FunctionSoftsplat(inp.cuda(), flow.cuda()).cpu(), softsplat_ref.function_softsplat_count(inp, flow))
+
+
+def test_edge_cases_ragged_and_degenerate():
+    from motif_b200 import softsplat_count_cp
+    from motif_b200.softsplat_cp import FunctionSoftsplat
+
+    # 1x1 image, single row, single column; everything flying out of the frame; many-to-one collisions
+    for (n, c, h, w) in [(1, 1, 1, 1), (1, 3, 1, 17), (2, 2, 19, 1), (1, 130, 5, 7)]:
+        gen = torch.Generator().manual_seed(h * 100 + w)
+        inp = torch.randn(n, c, h, w, generator=gen)
+        flow = torch.randn(n, 2, h, w, generator=gen) * 2
+        ro, _ = softsplat_ref.function_softsplat(inp, flow, None, "summation")
+        o, _ = FunctionSoftsplat(inp.cuda(), flow.cuda(), None, "summation")
+        assert (o.cpu() - ro).abs().max().item() < 1e-5
+    inp = torch.randn(1, 2, 8, 8)
+    out_of_frame = torch.full((1, 2, 8, 8), 100.0)
+    o, _ = FunctionSoftsplat(inp.cuda(), out_of_frame.cuda(), None, "summation")
+    assert o.abs().max().item() == 0.0
+    # all 64 sources land on one destination: 64 contributions > 8 bin slots -> overflow path
+    xs = torch.arange(8.0).view(1, 1, 8).expand(1, 8, 8)
+    ys = torch.arange(8.0).view(1, 8, 1).expand(1, 8, 8)
+    collide = torch.stack([3.0 - xs, 4.0 - ys], 1)
+    ro, _ = softsplat_ref.function_softsplat(inp, collide, None, "summation")
+    o, _ = FunctionSoftsplat(inp.cuda(), collide.cuda(), None, "summation")
+    assert (o.cpu() - ro).abs().max().item() < 1e-4
+    cnt = softsplat_count_cp.FunctionSoftsplat(inp.cuda(), collide.cuda())
+    assert cnt[0, 0, 4, 3].item() == 64.0
+    # non-finite flow is skipped, not trapped
+    bad = torch.zeros(1, 2, 8, 8)
+    bad[0, 0, 2, 2] = float("nan")
+    bad[0, 1, 5, 5] = float("inf")
+    o, _ = FunctionSoftsplat(inp.cuda(), bad.cuda(), None, "summation")
+    ref = inp.clone()
+    ref[0, :, 2, 2] = 0
+    ref[0, :, 5, 5] = 0
+    assert torch.equal(o.cpu(), ref)
+
+
+def test_full_size_properties_adobe_shape():
+    """BASELINE size (720x1280, C=130): size-independent properties instead of the (slow) oracle."""
+    from motif_b200 import softsplat_count_cp
+    from motif_b200.softsplat_cp import FunctionSoftsplat, _splat
+
+    torch.manual_seed(0)
+    n, c, h, w = 1, 130, 720, 1280
+    inp = torch.randn(n, c, h, w, device="cuda")
+    low = torch.randn(n, 2, h // 16, w // 16, device="cuda") * 6
+    flow = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False).contiguous()
+    metric = -torch.rand(n, 1, h, w, device="cuda")
+    out, norm = FunctionSoftsplat(inp, flow, metric, "softmax")
+    # (1) identity flow reproduces in * exp(metric)
+    zero = torch.zeros_like(flow)
+    o0, n0 = FunctionSoftsplat(inp, zero, metric, "softmax")
+    assert torch.equal(o0, inp * metric.exp()) or (o0 - inp * metric.exp()).abs().max().item() < 1e-6
+    # (2) linearity in the input
+    o2, _ = FunctionSoftsplat(2 * inp, flow, metric, "softmax")
+    assert (o2 - 2 * out).abs().max().item() < 1e-4
+    # (3) agreement with the float-atomic scatter of the same inputs
+    oa = _splat(inp, flow, metric, 3, atomic=True)
+    assert (torch.cat([out, norm], 1) - oa).abs().max().item() < 1e-3
+    # (4) the normaliser of 'average' with in-frame mass equals the count-weighted footprint: sum(norm) <= #pixels
+    _, navg = FunctionSoftsplat(inp[:, :1], flow, None, "average")
+    assert navg.sum().item() <= h * w * 1.0001
+    cnt = softsplat_count_cp.FunctionSoftsplat(inp, flow)
+    assert cnt.sum().item() <= 4 * h * w and torch.equal(cnt, cnt.round())
+    # (5) deterministic: two runs are bit-identical (no float atomics on the common path)
+    out_b, norm_b = FunctionSoftsplat(inp, flow, metric, "softmax")
+    few = cnt <= 8
+    assert torch.equal(out[few.expand_as(out)], out_b[few.expand_as(out_b)])
+
+
+def test_module_wrappers_and_contract():
+    from motif_b200.softsplat_count_cp import Softsplat_Count
+    from motif_b200.softsplat_cp import Softsplat
+    from motif_b200.softsplat_max_cp import Softsplat_Max
+
+    x = torch.rand(2, 5, 9, 11, device="cuda")
+    f = torch.randn(2, 2, 9, 11, device="cuda")
+    z = -torch.rand(2, 1, 9, 11, device="cuda")
+    out, norm = Softsplat()(x, f, z)
+    assert out.shape == (2, 5, 9, 11) and norm.shape == (2, 1, 9, 11)
+    assert norm.data_ptr() == out.data_ptr() + 5 * 9 * 11 * 4  # two views of one [N,C+1,H,W] buffer, like the reference
+    assert Softsplat_Max()(z.exp(), f).min().item() >= 1.0
+    assert Softsplat_Count()(z, f).shape == (2, 1, 9, 11)
+    # non-contiguous inputs are made contiguous like the reference wrapper does (softsplat_cp.py:232-233)
+    out2, _ = Softsplat()(x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2), f, z)
+    assert torch.equal(out2, out)
