@@ -1,8 +1,10 @@
 """Seeded synthetic inputs for benchmarks and smoke runs (no datasets or checkpoints are reachable).
 
 ``synthetic_params`` draws the three hot-path SIREN MLPs in the ``best.pth`` key layout with the
-reference's initialisation rule (``SIREN.py:35-42, 63-67``) times a gain, so that sine arguments,
-flows of a few HR pixels and a non-degenerate ``exp(z)`` are exercised.  ``synthetic_latents`` draws
+reference's initialisation rule (``SIREN.py:35-42, 63-67``): hidden layers at the reference scale,
+first layers x4, RGB centred in the clamp range and ``z_raw`` switching sign, so that sine arguments,
+flows of a few HR pixels and a non-degenerate ``exp(z)`` are exercised while the fp32 problem stays
+well-conditioned.  ``synthetic_latents`` draws
 smooth LR latents of the encoder's output shapes (``Ours.py:601-638``).
 """
 from __future__ import annotations
@@ -26,7 +28,7 @@ WORKLOADS = {
 }
 
 
-def synthetic_params(seed=0, weight_gain=2.0, first_gain=10.0, alpha=-1.0, rgb_bias=0.5, rgb_gain=3.0):
+def synthetic_params(seed=0, weight_gain=1.0, first_gain=4.0, alpha=-20.0, rgb_bias=0.5, rgb_gain=3.0, z_bias=0.03):
     g = torch.Generator().manual_seed(seed)
     p = {}
     for name, (fin, hidden, fout) in SPECS.items():
@@ -40,6 +42,7 @@ def synthetic_params(seed=0, weight_gain=2.0, first_gain=10.0, alpha=-1.0, rgb_b
             p[key + "bias"] = (torch.rand(k_out, generator=g) * 2 - 1) / math.sqrt(k_in)
     p["synth_net.net.4.weight"] *= rgb_gain
     p["synth_net.net.4.bias"] = torch.tensor([rgb_bias - 0.1, rgb_bias, rgb_bias + 0.1])
+    p["flow_imnet.net.3.bias"][2] = z_bias
     p["alpha"] = torch.ones(1) * alpha
     return p
 

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 from . import softsplat_ref as S
 
-__all__ = ["make_coord", "siren", "query_geometry", "decode", "SIREN_SPECS", "random_params"]
+__all__ = ["make_coord", "siren", "query_geometry", "decode", "SIREN_SPECS", "random_params", "count_unstable_mask", "REALISTIC"]
 
 # (in_features, hidden widths, out_features) -- Ours.py:470-471, 487-491
 SIREN_SPECS = {
@@ -251,7 +251,7 @@ def decode(
 
 
 def random_params(seed: int = 0, weight_gain: float = 1.0, alpha: float = -20.0, first_gain: Optional[float] = None,
-                  rgb_bias: Optional[float] = None, rgb_gain: float = 1.0):
+                  rgb_bias: Optional[float] = None, rgb_gain: float = 1.0, z_bias: Optional[float] = None):
     """Seeded synthetic hot-path weights in the ``best.pth`` key layout.
 
     ``weight_gain=1`` reproduces the reference initialisation (``SIREN.py:35-42, 63-67``
@@ -281,5 +281,36 @@ def random_params(seed: int = 0, weight_gain: float = 1.0, alpha: float = -20.0,
     if rgb_bias is not None:  # centre the synthetic RGB inside the clamp range
         p["synth_net.net.4.bias"] = torch.tensor([rgb_bias - 0.1, rgb_bias, rgb_bias + 0.1])
     p["synth_net.net.4.weight"] = p["synth_net.net.4.weight"] * rgb_gain
+    if z_bias is not None:  # make relu(z_raw) switch on and off across the image
+        p["flow_imnet.net.3.bias"][2] = z_bias
     p["alpha"] = torch.ones(1) * alpha
     return p
+
+
+# Non-degenerate but well-conditioned synthetic weights used by the parity tests: reference SIREN scale for
+# the hidden layers, first layers x4, RGB centred in the clamp range, z_raw switching sign, alpha as
+# initialised by the reference (Ours.py:509).
+REALISTIC = dict(weight_gain=1.0, first_gain=4.0, alpha=-20.0, rgb_bias=0.5, rgb_gain=3.0, z_bias=0.03)
+
+
+def count_unstable_mask(flow_hr: torch.Tensor, B: int, N: int, eps: float = 2.5e-4) -> torch.Tensor:
+    """Destination pixels at which the REFERENCE FUNCTION ITSELF is discontinuous in the flow.
+
+    The count splat (``softsplat_count_cp.py:25-50``) adds 1 to the four corners of
+    ``floor(position)``: when a source lands within ``eps`` pixels of an integer coordinate, an
+    arbitrarily small change of the flow (fp32 re-association inside ``flow_imnet``, TF32x3 vs fp32,
+    CUDA ``sinf`` vs the host's) moves a whole unit of ``count`` between neighbouring destinations, and
+    ``count/16`` and ``wz/count`` are ``synth_net`` inputs (``Ours.py:834``).  Two correct evaluations of
+    the reference differ by O(1e-2) in RGB at such pixels, so the 1e-3 gate is applied to the others.
+    ``flow_hr`` is ``[2*B*N, 2, HH, WW]`` (reference-major); returns bool ``[N, B, 1, HH, WW]``.
+    """
+    base = S.function_softsplat_count(flow_hr[:, :1], flow_hr)
+    bad = torch.zeros_like(base, dtype=torch.bool)
+    for sx in (-eps, eps):
+        for sy in (-eps, eps):
+            f = flow_hr.clone()
+            f[:, 0] += sx
+            f[:, 1] += sy
+            bad |= S.function_softsplat_count(f[:, :1], f) != base
+    HH, WW = bad.shape[-2:]
+    return bad.reshape(2, B, N, 1, HH, WW).any(0).permute(1, 0, 2, 3, 4)

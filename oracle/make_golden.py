@@ -113,7 +113,7 @@ def decoder_case(name, lr_hw, scale, times, batch, use_raft, seed, gain, first_g
         model.flow_predictor = _SmoothFlow(seed + 7, magnitude=3.0)
     if gain is not None:
         _load_hot_params(model, decoder_ref.random_params(seed=seed + 11, weight_gain=gain, first_gain=first_gain,
-                                                          alpha=alpha, rgb_bias=0.5, rgb_gain=4.0))
+                                                          alpha=alpha, rgb_bias=0.5, rgb_gain=3.0, z_bias=0.03))
     torch.manual_seed(seed + 1)
     h, w = lr_hw
     low = torch.rand(batch, 2, 3, max(h // 4, 2), max(w // 4, 2))
@@ -136,10 +136,12 @@ def decoder_case(name, lr_hw, scale, times, batch, use_raft, seed, gain, first_g
 def decoder_cases():
     # reference RAFT, reference default initialisation (alpha = -20: exp(z) ~ 1)
     decoder_case("decoder_raft", (32, 48), 4, [0.25, 0.5], 1, True, seed=0, gain=None, first_gain=None, alpha=None)
-    # O(1)-scaled SIREN weights, alpha=-1, three timestamps
-    decoder_case("decoder_x4", (16, 24), 4, [0.125, 0.5, 0.875], 1, False, seed=1, gain=2.0, first_gain=20.0, alpha=-1.0)
+    # non-degenerate variant: first layers x4, RGB centred in the clamp range, z switching on/off (alpha=-20
+    # as initialised by the reference, Ours.py:509); hidden layers keep the reference SIREN scale -- larger
+    # hidden gains make the fp32 reference itself ill-conditioned (1-ulp weight changes move flows by >1e-3 px)
+    decoder_case("decoder_x4", (16, 24), 4, [0.125, 0.5, 0.875], 1, False, seed=1, gain=1.0, first_gain=4.0, alpha=-20.0)
     # non-integer scale (round(H*3.5)), two clips: exercises index ties and batch ordering
-    decoder_case("decoder_x3p5_b2", (16, 20), 3.5, [0.3, 0.75], 2, False, seed=2, gain=3.0, first_gain=30.0, alpha=-2.0)
+    decoder_case("decoder_x3p5_b2", (16, 20), 3.5, [0.3, 0.75], 2, False, seed=2, gain=1.0, first_gain=4.0, alpha=-20.0)
 
 
 if __name__ == "__main__":
