@@ -150,6 +150,10 @@ size_t motif_decode_workspace_bytes(int B, int N, int H, int W, int HH, int WW);
  * per timestamp flow_imnet -> 3 splats of both references -> blend -> synth_net -> clamp. */
 int motif_decode(const motif_decode_t* args, void* stream);
 
+/* Self-test of the tcgen05 path on one tile: d[128][64] = x[128][64] * w[64][64]^T with `terms` = 1
+ * (plain TF32) or 3 (error-compensated 3xTF32).  scratch: >= 32 KiB of device memory. */
+int motif_tc_selftest(const float* x, const float* w, float* d, float* scratch, int terms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

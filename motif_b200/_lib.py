@@ -32,6 +32,7 @@ EXPORTS = [
     "motif_pack_latents",
     "motif_decode_workspace_bytes",
     "motif_decode",
+    "motif_tc_selftest",
 ]
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3}
@@ -102,6 +103,8 @@ def _declare(lib):
     lib.motif_pack_latents.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_decode_workspace_bytes.restype = c_size_t
     lib.motif_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.motif_tc_selftest.restype = c_int
+    lib.motif_tc_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     lib.motif_decode.restype = c_int
     lib.motif_decode.argtypes = [POINTER(DecodeT), c_void_p]
 

@@ -77,5 +77,10 @@ extern "C" long long motif_launch_count(void) { return g_launches.load(); }
 extern "C" void motif_reset_launch_count(void) { g_launches.store(0); }
 
 extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
-  return decode_simt(args, (cudaStream_t)stream);
+  if (int rc = check_decode(args)) return rc;
+  switch (args->precision) {
+    case MOTIF_PRECISION_TF32X3: return decode_tc(args, (cudaStream_t)stream);
+    case MOTIF_PRECISION_FP32: return decode_simt(args, (cudaStream_t)stream);
+    default: return fail(MOTIF_E_BADARG, "decode: unknown precision %d", args->precision);
+  }
 }

@@ -52,6 +52,7 @@ struct DecodeScratch {
   float* acc_side;
   float* acc_max;
   float* wpack;
+  float* wimg;  // tensor-core weight block images (tc_pack.cuh)
 };
 
 // Offsets (in floats) into the packed weight image.  K is split into 64-wide blocks that multiply
@@ -96,5 +97,8 @@ struct WeightPack {
 int pack_weights(const motif_decode_t* a, float* wpack, cudaStream_t st);
 int decode_layout(int B, int N, int H, int W, int HH, int WW, DecodeScratch* s, char* base, size_t* bytes);
 int decode_simt(const motif_decode_t* a, cudaStream_t st);
+int decode_tc(const motif_decode_t* a, cudaStream_t st);
+int check_decode(const motif_decode_t* a);
+size_t tc_image_bytes();
 
 }  // namespace motif

@@ -465,7 +465,8 @@ int decode_layout(int B, int N, int H, int W, int HH, int WW, DecodeScratch* s, 
   float* as = take(sizeof(float) * B * qs * 4);
   float* ax = take(sizeof(float) * B * qs);
   float* wp = take(sizeof(float) * WeightPack::total);
-  if (s) *s = DecodeScratch{imf, am, as, ax, wp};
+  float* wi = take(tc_image_bytes());
+  if (s) *s = DecodeScratch{imf, am, as, ax, wp, wi};
   if (bytes) *bytes = off;
   return 0;
 }
@@ -474,7 +475,7 @@ __global__ void fill_ones_kernel(float* p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 1.0f;
 }
 
-static int check_decode(const motif_decode_t* a) {
+int check_decode(const motif_decode_t* a) {
   MOTIF_REQUIRE(a != nullptr, "decode: null args");
   const motif_geom_t& g = a->geom;
   MOTIF_REQUIRE(g.B > 0 && g.N > 0 && g.H > 0 && g.W > 0 && g.HH > 0 && g.WW > 0, "decode: non-positive size");
@@ -487,7 +488,6 @@ static int check_decode(const motif_decode_t* a) {
 }
 
 int decode_simt(const motif_decode_t* a, cudaStream_t st) {
-  if (int rc = check_decode(a)) return rc;
   const motif_geom_t& g = a->geom;
   DecodeScratch sc;
   size_t need = 0;

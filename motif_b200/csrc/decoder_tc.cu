@@ -1,0 +1,792 @@
+// Space-time local implicit decoder on the 5th-generation tensor cores (sm_100a): the three SIREN MLPs of
+// Ours.py:470-471, 487-491 as tcgen05.mma kind::tf32 with fp32 accumulators in tensor memory, error
+// compensated (3xTF32: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo) so that products are fp32-equivalent.
+//
+// One persistent CTA per SM, 12 warps, warp-specialised:
+//   warp 0      weight producer: streams 64x64 weight "block images" (pre-split hi/lo, pre-swizzled; tc_pack.cu)
+//               from L2 into a 5-slot shared-memory ring with cp.async.bulk + mbarrier complete_tx
+//   warp 1      MMA issuer: one elected thread issues every tcgen05.mma of the CTA (M = 128 pixels, N = 64, K = 8)
+//   warp 2      TMEM allocation (all 512 columns), otherwise idle;  warp 3 idle
+//   warps 4-7   pixel tile 0: thread i owns pixel row i == TMEM lane i.  Stages the A operand into TMEM
+//   warps 8-11  pixel tile 1  (tcgen05.st, hi and lo halves), reads accumulators back (tcgen05.ld), applies bias,
+//               sin(30 x), rank-1 input terms, the 256 -> 3 output layers on CUDA cores, and the scatter / blend.
+// Two pixel tiles are in flight per CTA and share every weight block, so the tensor pipe works on one tile
+// while the other tile's activation epilogue runs.  Activations never leave the SM: TMEM -> registers -> TMEM.
+//
+// Per tile the 256 TMEM columns are:  [0,64) A_hi  [64,128) A_lo  [128,192) D0  [192,256) D1.
+#include "decoder_common.cuh"
+#include "tc_common.cuh"
+#include "tc_pack.cuh"
+
+namespace motif {
+
+using namespace tc;
+
+constexpr int kRing = 5;                 // weight ring slots (32 KB each)
+constexpr int kTcThreads = 384;          // 12 warps
+constexpr int kEpiWarp0 = 4;             // first epilogue warp
+constexpr int kTileCols = 256;           // TMEM columns per pixel tile
+constexpr uint32_t kColAhi = 0, kColAlo = 64, kColD0 = 128;
+
+// Weight image indices (program order per network)
+constexpr int kImgF = 0, kNumF = 6;      // flow_imnet: a0, a1, a2 chunk 0..3
+constexpr int kImgI = 6, kNumI = 10;     // imnet: a0, a1, (a2 chunk c, a3 k-block c) x 4
+constexpr int kImgS = 16, kNumS = 9;     // synth_net: a0a, a0b, a0c, a1, a2, a3 chunk 0..3
+constexpr int kNumImages = 25;
+
+struct Step {
+  int dbuf;        // accumulator buffer: D0 (0) or D1 (1)
+  bool a_new;      // the epilogue restaged the A operand for this step: wait a_ready
+  bool acc;        // accumulate into D (continuation of a K loop)
+  bool commit_d;   // D complete after this step: commit d_ready[dbuf]
+  bool commit_a;   // more K blocks follow and need a restaged A: commit a_free
+  int terms;       // 3 = error-compensated, 1 = plain TF32 (A_hi * B_hi)
+  bool a_in_d0;    // A operand is read from the D0 columns (imnet output layer), hi only
+};
+
+struct Barriers {
+  uint64_t w_full[kRing], w_empty[kRing];
+  uint64_t a_ready[2], a_free[2];
+  uint64_t d_ready[2][2], d_free[2][2];
+  uint32_t tmem_base;
+};
+
+struct TcSmem {
+  unsigned char ring[kRing][kBlockImageBytes];  // must stay first: 1024-byte aligned swizzle atoms
+  float consts[2048];                           // per-network epilogue constants (biases, rank-1 columns, output layer)
+  Barriers bars;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// warp 0: weight producer
+// ------------------------------------------------------------------------------------------------------
+template <int NSTEPS>
+__device__ __forceinline__ void producer_loop(TcSmem& sm, const float* __restrict__ wimg, int img0, const Step (&prog)[NSTEPS], int n_iters) {
+  uint32_t g = 0;
+  for (int it = 0; it < n_iters; ++it) {
+#pragma unroll 1
+    for (int s = 0; s < NSTEPS; ++s, ++g) {
+      const int slot = g % kRing;
+      const uint32_t use = g / kRing;
+      mbar_wait(&sm.bars.w_empty[slot], (use & 1) ^ 1);
+      const uint32_t bytes = prog[s].terms == 3 ? kBlockImageBytes : kBlockHalfBytes;
+      mbar_arrive_expect_tx(&sm.bars.w_full[slot], bytes);
+      bulk_g2s(sm.ring[slot], reinterpret_cast<const unsigned char*>(wimg) + (size_t)(img0 + s) * kBlockImageBytes, bytes, &sm.bars.w_full[slot]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// warp 1: MMA issuer (one thread)
+// ------------------------------------------------------------------------------------------------------
+template <int NSTEPS>
+__device__ __forceinline__ void issuer_loop(TcSmem& sm, const Step (&prog)[NSTEPS], int n_iters, uint32_t tmem_base) {
+  const uint32_t idesc = idesc_tf32(128, 64);
+  uint32_t g = 0;
+  uint32_t ph_aready[2] = {0, 0};
+  uint32_t ph_dfree[2][2] = {{1, 1}, {1, 1}};  // first wait passes: buffers start free
+  for (int it = 0; it < n_iters; ++it) {
+#pragma unroll 1
+    for (int s = 0; s < NSTEPS; ++s, ++g) {
+      const Step st = prog[s];
+      const int slot = g % kRing;
+      mbar_wait(&sm.bars.w_full[slot], (g / kRing) & 1);
+      const uint32_t bhi = smem_u32(sm.ring[slot]);
+      const uint32_t blo = bhi + kBlockHalfBytes;
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const uint32_t tbase = tmem_base + tile * kTileCols;
+        if (st.a_new) {
+          mbar_wait(&sm.bars.a_ready[tile], ph_aready[tile]);
+          ph_aready[tile] ^= 1;
+        }
+        if (!st.acc) {
+          mbar_wait(&sm.bars.d_free[tile][st.dbuf], ph_dfree[tile][st.dbuf]);
+          ph_dfree[tile][st.dbuf] ^= 1;
+        }
+        tc_fence_after();
+        const uint32_t dcol = tbase + kColD0 + 64 * st.dbuf;
+        const uint32_t a_hi = tbase + (st.a_in_d0 ? kColD0 : kColAhi);
+        bool acc = st.acc;
+        for (int term = 0; term < st.terms; ++term) {
+          const uint32_t acol = (term == 1) ? tbase + kColAlo : a_hi;
+          const uint32_t bbase = (term == 2) ? blo : bhi;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            mma_tf32_ts(dcol, acol + ks * 8, smem_desc_sw128(bbase + (ks >> 2) * 8192 + (ks & 3) * 32), idesc, acc);
+            acc = true;
+          }
+        }
+        if (st.commit_d) mma_commit(&sm.bars.d_ready[tile][st.dbuf]);
+        if (st.commit_a) mma_commit(&sm.bars.a_free[tile]);
+      }
+      mma_commit(&sm.bars.w_empty[slot]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// epilogue helpers (128 threads per tile; thread <-> TMEM lane)
+// ------------------------------------------------------------------------------------------------------
+struct EpiCtx {
+  TcSmem* sm;
+  int tile;            // 0 / 1
+  uint32_t lane_addr;  // TMEM address of this thread's lane, column 0 of its tile
+  uint32_t ph_dready[2];
+  uint32_t ph_afree;
+};
+
+// sin(30 * pre) with pre folded:  v = pre * 30/(2 pi) (revolutions), reduced to [-0.5, 0.5], MUFU.SIN.
+// Absolute error ~1e-6 (fp32 rounding of v plus sin.approx), far below the TF32x3 accumulation noise x 30.
+constexpr float kRevPerUnit = 4.774648292756860f;  // 30 / (2 pi)
+__device__ __forceinline__ float sin_rev(float v) {
+  const float k = (v + 12582912.0f) - 12582912.0f;  // round to nearest integer (|v| < 2^22)
+  const float u = v - k;
+  return __sinf(u * 6.283185307179586f);
+}
+
+__device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float h = tf32_rna(v[j]);
+    hi[j] = __float_as_uint(h);
+    lo[j] = __float_as_uint(tf32_rna(v[j] - h));
+  }
+  tmem_st16(taddr_hi, hi);
+  tmem_st16(taddr_lo, lo);
+}
+
+__device__ __forceinline__ void publish_a(EpiCtx& c) {
+  tmem_wait_st();
+  tc_fence_before();
+  mbar_arrive(&c.sm->bars.a_ready[c.tile]);
+}
+
+__device__ __forceinline__ void wait_d(EpiCtx& c, int dbuf) {
+  mbar_wait(&c.sm->bars.d_ready[c.tile][dbuf], c.ph_dready[dbuf]);
+  c.ph_dready[dbuf] ^= 1;
+  tc_fence_after();
+}
+__device__ __forceinline__ void release_d(EpiCtx& c, int dbuf) {
+  tc_fence_before();
+  mbar_arrive(&c.sm->bars.d_free[c.tile][dbuf]);
+}
+__device__ __forceinline__ void wait_a_free(EpiCtx& c) {
+  mbar_wait(&c.sm->bars.a_free[c.tile], c.ph_afree);
+  c.ph_afree ^= 1;
+  tc_fence_after();
+}
+
+__device__ __forceinline__ void load16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld16(taddr, r);
+  tmem_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// Stage a 64-float row held in registers as the next A operand.
+__device__ __forceinline__ void stage_row(EpiCtx& c, const float (&h)[64]) {
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = h[c0 + j];
+    split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
+  }
+  publish_a(c);
+}
+
+__device__ __forceinline__ void ldg_row64(const float* __restrict__ row, float (&h)[64]) {
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + k4);
+    h[4 * k4 + 0] = v.x;
+    h[4 * k4 + 1] = v.y;
+    h[4 * k4 + 2] = v.z;
+    h[4 * k4 + 3] = v.w;
+  }
+}
+
+// Plain 64 -> 64 sine layer epilogue: D[dbuf] -> sin(30 (D + bias)) -> A.  `cb` = bias * 30/(2 pi) (smem).
+__device__ __forceinline__ void sine_epilogue(EpiCtx& c, int dbuf, const float* __restrict__ cb) {
+  wait_d(c, dbuf);
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+    load16(c.lane_addr + kColD0 + 64 * dbuf + c0, v);
+    if (c0 == 48) release_d(c, dbuf);
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = *reinterpret_cast<const float4*>(cb + c0 + 4 * j4);
+      v[4 * j4 + 0] = sin_rev(fmaf(v[4 * j4 + 0], kRevPerUnit, b.x));
+      v[4 * j4 + 1] = sin_rev(fmaf(v[4 * j4 + 1], kRevPerUnit, b.y));
+      v[4 * j4 + 2] = sin_rev(fmaf(v[4 * j4 + 2], kRevPerUnit, b.z));
+      v[4 * j4 + 3] = sin_rev(fmaf(v[4 * j4 + 3], kRevPerUnit, b.w));
+    }
+    split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
+  }
+  publish_a(c);
+}
+
+// 64 hidden units of a 64 -> 256 sine layer followed by a 256 -> 3 linear layer on CUDA cores.
+// cw[j] = (bias2_j * 30/2pi, w3[0][j], w3[1][j], w3[2][j]) for the 64 units of this chunk (smem).
+__device__ __forceinline__ void sine_out3_epilogue(EpiCtx& c, int dbuf, const float4* __restrict__ cw, float& o0, float& o1, float& o2) {
+  wait_d(c, dbuf);
+#pragma unroll 1
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+    load16(c.lane_addr + kColD0 + 64 * dbuf + c0, v);
+    if (c0 == 48) release_d(c, dbuf);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 w = cw[c0 + j];
+      const float s = sin_rev(fmaf(v[j], kRevPerUnit, w.x));
+      o0 = fmaf(s, w.y, o0);
+      o1 = fmaf(s, w.z, o1);
+      o2 = fmaf(s, w.w, o2);
+    }
+  }
+}
+
+__device__ __forceinline__ void init_barriers(TcSmem& sm) {
+  for (int i = 0; i < kRing; ++i) {
+    mbar_init(&sm.bars.w_full[i], 1);
+    mbar_init(&sm.bars.w_empty[i], 1);
+  }
+  for (int t = 0; t < 2; ++t) {
+    mbar_init(&sm.bars.a_ready[t], 128);
+    mbar_init(&sm.bars.a_free[t], 1);
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&sm.bars.d_ready[t][d], 1);
+      mbar_init(&sm.bars.d_free[t][d], 128);
+    }
+  }
+  fence_mbar_init();
+}
+
+// Common prologue / epilogue of the three kernels.
+__device__ __forceinline__ uint32_t tc_setup(TcSmem& sm) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) init_barriers(sm);
+  if (warp == 2) tmem_alloc<512>(&sm.bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return sm.bars.tmem_base;
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 2) tmem_dealloc<512>(tmem_base);
+}
+
+__device__ __forceinline__ EpiCtx make_epi(TcSmem& sm, uint32_t tmem_base) {
+  const int warp = threadIdx.x >> 5;
+  EpiCtx c;
+  c.sm = &sm;
+  c.tile = (warp - kEpiWarp0) >> 2;
+  c.lane_addr = tmem_base + c.tile * kTileCols + ((uint32_t)((warp & 3) * 32) << 16);
+  c.ph_dready[0] = c.ph_dready[1] = 0;
+  c.ph_afree = 0;
+  return c;
+}
+__device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
+
+// ======================================================================================================
+// flow_imnet + forward splats.  Tile 0 = reference frame 0, tile 1 = reference frame 1 of the same 128 pixels.
+// ======================================================================================================
+__constant__ Step kProgF[kNumF] = {
+    {0, true, false, true, false, 3, false},   // layer 0 (64 gathered features; t, rel as rank-1 terms)
+    {0, true, false, true, false, 3, false},   // layer 1
+    {0, true, false, true, false, 3, false},   // layer 2 units 0..63
+    {1, false, false, true, false, 3, false},  //         units 64..127
+    {0, false, false, true, false, 3, false},  //         units 128..191
+    {1, false, false, true, false, 3, false},  //         units 192..255
+};
+
+// consts layout (floats): [0,256) e0 as float4 per unit (c0 = (bias + w_t t) * R, w_rely * R, w_relx * R, 0)
+//                         [256,320) bias1 * R   [320,1344) float4 per hidden unit (bias2 * R, w3[0], w3[1], w3[2])   [1344,1347) bias3
+__global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom_t g, int B, int N, int n, int b, float t, float alpha,
+                                                                     const float* __restrict__ feat, const float* __restrict__ flow_feat,
+                                                                     const float* __restrict__ imf, const float* __restrict__ wp,
+                                                                     const float* __restrict__ wimg, DecodeScratch sc, float* __restrict__ flow_out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW;
+  const int n_tiles = (qs + 127) / 128;
+  const int n_iters = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * i);
+    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(fmaf(e.y, t, e.x) * kRevPerUnit, e.z * kRevPerUnit, e.w * kRevPerUnit, 0.f);
+    sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kRevPerUnit;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<float4*>(sm.consts + 320)[i] = make_float4(wp[WeightPack::f_b2 + i] * kRevPerUnit, wp[WeightPack::f_a3 + i],
+                                                                wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 512 + i]);
+  if (threadIdx.x < 3) sm.consts[1344 + threadIdx.x] = wp[WeightPack::f_b3 + threadIdx.x];
+  const uint32_t tmem_base = tc_setup(sm);
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(sm, wimg, kImgF, kProgF, n_iters);
+  } else if (warp == 1) {
+    if (lane == 0) issuer_loop(sm, kProgF, n_iters, tmem_base);
+  } else if (warp >= kEpiWarp0) {
+    EpiCtx c = make_epi(sm, tmem_base);
+    const int r = c.tile;  // reference frame
+    const int rb = r * B + b;
+    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
+    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile_id = blockIdx.x + it * gridDim.x;
+      const int q = tile_id * 128 + epi_row();
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      const int qy = qc / g.WW, qx = qc % g.WW;
+      const Query qu = make_query(qy, qx, g);
+      const size_t lr = (size_t)qu.iy * g.W + qu.ix;
+      {
+        float h[64];
+        ldg_row64(flow_feat + ((size_t)rb * g.H * g.W + lr) * 64, h);
+        stage_row(c, h);
+      }
+      // layer 0 epilogue: rank-1 terms of t (folded into c0), rel_y, rel_x
+      wait_d(c, 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        load16(c.lane_addr + kColD0 + c0, v);
+        if (c0 == 48) release_d(c, 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 e = e0[c0 + j];
+          v[j] = sin_rev(fmaf(v[j], kRevPerUnit, fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, e.x))));
+        }
+        split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
+      }
+      publish_a(c);
+      sine_epilogue(c, 0, sm.consts + 256);
+      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, cw + 64 * ch, dx, dy, zraw);
+
+      // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  then the three splats
+      const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
+      const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
+      const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
+      const float e = expf(z);
+      if (live && flow_out != nullptr) {
+        float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
+        fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
+        fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
+      }
+      Footprint f = footprint(qx, qy, fx, fy);
+      if (!live) f.finite = false;
+      for (int p = 0; p < 32; ++p) {
+        if (!__shfl_sync(0xffffffffu, (int)f.finite, p)) continue;
+        const int sx0 = __shfl_sync(0xffffffffu, f.x0, p), sy0 = __shfl_sync(0xffffffffu, f.y0, p);
+        const float se = __shfl_sync(0xffffffffu, e, p);
+        const int sq = __shfl_sync(0xffffffffu, q, p);
+        const size_t slr = __shfl_sync(0xffffffffu, (unsigned long long)lr, p);
+        const float sdx = __shfl_sync(0xffffffffu, dx, p), sdy = __shfl_sync(0xffffffffu, dy, p);
+        float w4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w4[k] = __shfl_sync(0xffffffffu, f.w[k], p);
+        const float* srow = lane < 16 ? imf + ((size_t)rb * qs + sq) * 64 + 4 * lane
+                                      : feat + ((size_t)rb * g.H * g.W + slr) * 64 + 4 * (lane - 16);
+        float4 v = __ldg(reinterpret_cast<const float4*>(srow));
+        v.x = __fmul_rn(v.x, se);
+        v.y = __fmul_rn(v.y, se);
+        v.z = __fmul_rn(v.z, se);
+        v.w = __fmul_rn(v.w, se);
+        const float edx = __fmul_rn(sdx, se), edy = __fmul_rn(sdy, se);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cx = sx0 + (k & 1), cy = sy0 + (k >> 1);
+          if ((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH)) continue;
+          const size_t d = (size_t)b * qs + (size_t)cy * g.WW + cx;
+          const float wk = w4[k];
+          red_add_v4(sc.acc_main + d * 128 + 4 * lane, __fmul_rn(v.x, wk), __fmul_rn(v.y, wk), __fmul_rn(v.z, wk), __fmul_rn(v.w, wk));
+          if (lane == 0) red_add_v4(sc.acc_side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), __fmul_rn(se, wk), 1.0f);
+          if (lane == 1) red_max_nonneg(sc.acc_max + d, __fmul_rn(se, wk));
+        }
+      }
+    }
+  }
+  tc_teardown(tmem_base);
+}
+
+// ======================================================================================================
+// blend + synth_net.  Tiles 0 / 1 are two consecutive 128-pixel tiles of the destination image.
+// ======================================================================================================
+__constant__ Step kProgS[kNumS] = {
+    {0, true, false, false, true, 3, false},   // layer 0, K block: blended imnet features (cols 0..63)
+    {0, true, true, false, true, 3, false},    //          K block: blended nearest features (cols 66..129)
+    {0, true, true, true, false, 3, false},    //          K block: residual latent (cols 133..196)
+    {0, true, false, true, false, 3, false},   // layer 1
+    {0, true, false, true, false, 3, false},   // layer 2
+    {0, true, false, true, false, 3, false},   // layer 3 units 0..63
+    {1, false, false, true, false, 3, false},
+    {0, false, false, true, false, 3, false},
+    {1, false, false, true, false, 3, false},
+};
+
+// consts: [0,512) e0 as 2 x float4 per unit: (bias * R, w_dx R, w_dy R, w_zmax R), (w_cnt R, w_wz R, w_t R, 0)
+//         [512,576) bias1 R   [576,640) bias2 R   [640,1664) float4 per hidden unit (bias3 R, w4[0], w4[1], w4[2])   [1664,1667) bias4
+__global__ void __launch_bounds__(kTcThreads, 1) synth_tc_kernel(motif_geom_t g, int B, int N, int n, int b, float t,
+                                                                const float* __restrict__ residual, const float* __restrict__ wp,
+                                                                const float* __restrict__ wimg, DecodeScratch sc, float* __restrict__ rgb,
+                                                                float* __restrict__ dbg_in) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW;
+  const int n_units = (qs + 255) / 256;
+  const int n_iters = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(wp + WeightPack::s_e0 + 8 * i);
+    const float4 c2 = *reinterpret_cast<const float4*>(wp + WeightPack::s_e0 + 8 * i + 4);
+    reinterpret_cast<float4*>(sm.consts)[2 * i] = make_float4(a.x * kRevPerUnit, a.y * kRevPerUnit, a.z * kRevPerUnit, a.w * kRevPerUnit);
+    reinterpret_cast<float4*>(sm.consts)[2 * i + 1] = make_float4(c2.x * kRevPerUnit, c2.y * kRevPerUnit, c2.z * kRevPerUnit, 0.f);
+    sm.consts[512 + i] = wp[WeightPack::s_b1 + i] * kRevPerUnit;
+    sm.consts[576 + i] = wp[WeightPack::s_b2 + i] * kRevPerUnit;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<float4*>(sm.consts + 640)[i] = make_float4(wp[WeightPack::s_b3 + i] * kRevPerUnit, wp[WeightPack::s_a4 + i],
+                                                                wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 512 + i]);
+  if (threadIdx.x < 3) sm.consts[1664 + threadIdx.x] = wp[WeightPack::s_b4 + threadIdx.x];
+  const uint32_t tmem_base = tc_setup(sm);
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(sm, wimg, kImgS, kProgS, n_iters);
+  } else if (warp == 1) {
+    if (lane == 0) issuer_loop(sm, kProgS, n_iters, tmem_base);
+  } else if (warp >= kEpiWarp0) {
+    EpiCtx c = make_epi(sm, tmem_base);
+    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
+    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 640);
+    const int bn = b * N + n;
+    for (int it = 0; it < n_iters; ++it) {
+      const int unit = blockIdx.x + it * gridDim.x;
+      const int q = unit * 256 + c.tile * 128 + epi_row();
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      const Query qu = make_query(qc / g.WW, qc % g.WW, g);
+      const size_t d = (size_t)b * qs + qc;
+
+      float4* side_p = reinterpret_cast<float4*>(sc.acc_side + d * 4);
+      const float4 side = *side_p;
+      const float zmax = sc.acc_max[d];
+      float4* main_p = reinterpret_cast<float4*>(sc.acc_main + d * 128);
+      // Ours.py:813-814, 826-829, 834
+      const float wz = side.z == 0.0f ? 1.0f : side.z;
+      const float cnt = side.w;
+      const float cnt_ = cnt == 0.0f ? 1.0f : cnt;
+      const float wz_ = wz == 1.0f ? 0.0f : wz;
+      const float x_dx = __fdiv_rn(side.x, wz), x_dy = __fdiv_rn(side.y, wz);
+      const float x_cnt = __fdiv_rn(cnt, 16.0f), x_wz = __fdiv_rn(wz_, cnt_);
+      float* dbg = (dbg_in && live) ? dbg_in + (size_t)bn * 198 * qs + q : nullptr;
+      if (dbg) {
+        dbg[(size_t)64 * qs] = x_dx;
+        dbg[(size_t)65 * qs] = x_dy;
+        dbg[(size_t)130 * qs] = zmax;
+        dbg[(size_t)131 * qs] = x_cnt;
+        dbg[(size_t)132 * qs] = x_wz;
+        dbg[(size_t)197 * qs] = t;
+      }
+      // layer 0: three K blocks, each staged after the previous block's MMAs released the A columns
+#pragma unroll 1
+      for (int kb = 0; kb < 3; ++kb) {
+        float h[64];
+        if (kb < 2) {
+#pragma unroll
+          for (int k4 = 0; k4 < 16; ++k4) {
+            const float4 v = main_p[16 * kb + k4];
+            h[4 * k4 + 0] = __fdiv_rn(v.x, wz);
+            h[4 * k4 + 1] = __fdiv_rn(v.y, wz);
+            h[4 * k4 + 2] = __fdiv_rn(v.z, wz);
+            h[4 * k4 + 3] = __fdiv_rn(v.w, wz);
+          }
+          if (live) {
+#pragma unroll
+            for (int k4 = 0; k4 < 16; ++k4) main_p[16 * kb + k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {
+          ldg_row64(residual + ((size_t)b * g.H * g.W + (size_t)qu.iy * g.W + qu.ix) * 64, h);
+        }
+        if (dbg) {
+          const int ch0 = kb == 0 ? 0 : (kb == 1 ? 66 : 133);
+#pragma unroll
+          for (int k = 0; k < 64; ++k) dbg[(size_t)(ch0 + k) * qs] = h[k];
+        }
+        if (kb > 0) wait_a_free(c);
+        stage_row(c, h);
+      }
+      if (live) {
+        *side_p = make_float4(0.f, 0.f, 0.f, 0.f);
+        sc.acc_max[d] = 1.0f;
+      }
+      // layer 0 epilogue with the six rank-1 inputs
+      wait_d(c, 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        load16(c.lane_addr + kColD0 + c0, v);
+        if (c0 == 48) release_d(c, 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 ea = e0[2 * (c0 + j)], eb = e0[2 * (c0 + j) + 1];
+          float pre = ea.x;
+          pre = fmaf(ea.y, x_dx, pre);
+          pre = fmaf(ea.z, x_dy, pre);
+          pre = fmaf(ea.w, zmax, pre);
+          pre = fmaf(eb.x, x_cnt, pre);
+          pre = fmaf(eb.y, x_wz, pre);
+          pre = fmaf(eb.z, t, pre);
+          v[j] = sin_rev(fmaf(v[j], kRevPerUnit, pre));
+        }
+        split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
+      }
+      publish_a(c);
+      sine_epilogue(c, 0, sm.consts + 512);
+      sine_epilogue(c, 0, sm.consts + 576);
+      float o0 = sm.consts[1664], o1 = sm.consts[1665], o2 = sm.consts[1666];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, cw + 64 * ch, o0, o1, o2);
+      if (live) {
+        float* out = rgb + ((size_t)(n * B + b) * 3) * qs + q;
+        out[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
+        out[(size_t)qs] = fminf(fmaxf(o1, 0.0f), 1.0f);
+        out[(size_t)2 * qs] = fminf(fmaxf(o2, 0.0f), 1.0f);
+      }
+    }
+  }
+  tc_teardown(tmem_base);
+}
+
+// ======================================================================================================
+// imnet.  Tile 0 = reference frame 0, tile 1 = reference frame 1.  D0 doubles as the (hi-only) A operand
+// of the 256 -> 64 output layer, whose accumulator lives in D1 across the four hidden-unit chunks.
+// ======================================================================================================
+__constant__ Step kProgI[kNumI] = {
+    {0, true, false, true, false, 3, false},   // layer 0
+    {0, true, false, true, false, 3, false},   // layer 1
+    {0, true, false, true, false, 3, false},   // layer 2 units 0..63            -> D0
+    {1, true, false, false, false, 1, true},   // layer 3 K block 0 (A = sin(D0)) -> D1
+    {0, false, false, true, false, 3, false},  // layer 2 units 64..127  (overwrites D0 after the MMA above read it)
+    {1, true, true, false, false, 1, true},
+    {0, false, false, true, false, 3, false},
+    {1, true, true, false, false, 1, true},
+    {0, false, false, true, false, 3, false},
+    {1, true, true, true, false, 1, true},     // last K block completes D1
+};
+
+// consts: [0,256) e0 float4 per unit (bias R, w_rely R, w_relx R, 0)  [256,320) bias1 R  [320,576) bias2 R  [576,640) bias3
+__global__ void __launch_bounds__(kTcThreads, 1) imnet_tc_kernel(motif_geom_t g, int B, int b, const float* __restrict__ feat,
+                                                                const float* __restrict__ wp, const float* __restrict__ wimg,
+                                                                float* __restrict__ imf) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW;
+  const int n_tiles = (qs + 127) / 128;
+  const int n_iters = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::i_e0 + 4 * i);
+    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(e.x * kRevPerUnit, e.y * kRevPerUnit, e.z * kRevPerUnit, 0.f);
+    sm.consts[256 + i] = wp[WeightPack::i_b1 + i] * kRevPerUnit;
+    sm.consts[576 + i] = wp[WeightPack::i_b3 + i];
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.consts[320 + i] = wp[WeightPack::i_b2 + i] * kRevPerUnit;
+  const uint32_t tmem_base = tc_setup(sm);
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(sm, wimg, kImgI, kProgI, n_iters);
+  } else if (warp == 1) {
+    if (lane == 0) issuer_loop(sm, kProgI, n_iters, tmem_base);
+  } else if (warp >= kEpiWarp0) {
+    EpiCtx c = make_epi(sm, tmem_base);
+    const int rb = c.tile * B + b;
+    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile_id = blockIdx.x + it * gridDim.x;
+      const int q = tile_id * 128 + epi_row();
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      const Query qu = make_query(qc / g.WW, qc % g.WW, g);
+      {
+        float h[64];
+        ldg_row64(feat + ((size_t)rb * g.H * g.W + (size_t)qu.iy * g.W + qu.ix) * 64, h);
+        stage_row(c, h);
+      }
+      wait_d(c, 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        load16(c.lane_addr + kColD0 + c0, v);
+        if (c0 == 48) release_d(c, 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 e = e0[c0 + j];
+          v[j] = sin_rev(fmaf(v[j], kRevPerUnit, fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, e.x))));
+        }
+        split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
+      }
+      publish_a(c);
+      sine_epilogue(c, 0, sm.consts + 256);
+      // layer 2 chunk -> sine -> rewritten in place (TF32-rounded) as the A operand of the output layer
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        wait_d(c, 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+          load16(c.lane_addr + kColD0 + c0, v);
+          uint32_t hi[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 320 + 64 * ch + c0 + 4 * j4);
+            hi[4 * j4 + 0] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 0], kRevPerUnit, bb.x))));
+            hi[4 * j4 + 1] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 1], kRevPerUnit, bb.y))));
+            hi[4 * j4 + 2] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 2], kRevPerUnit, bb.z))));
+            hi[4 * j4 + 3] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 3], kRevPerUnit, bb.w))));
+          }
+          tmem_st16(c.lane_addr + kColD0 + c0, hi);
+        }
+        release_d(c, 0);
+        publish_a(c);
+      }
+      // output layer accumulator
+      wait_d(c, 1);
+      float4* dst = reinterpret_cast<float4*>(imf + ((size_t)rb * qs + qc) * 64);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        load16(c.lane_addr + kColD0 + 64 + c0, v);
+        if (c0 == 48) release_d(c, 1);
+        if (live) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 576 + c0 + 4 * j4);
+            dst[(c0 >> 2) + j4] = make_float4(v[4 * j4] + bb.x, v[4 * j4 + 1] + bb.y, v[4 * j4 + 2] + bb.z, v[4 * j4 + 3] + bb.w);
+          }
+        }
+      }
+    }
+  }
+  tc_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+struct ImgJob {
+  int src_off, ldw, n0, k0;
+};
+struct ImgJobs {
+  ImgJob j[kNumImages];
+};
+
+__global__ void pack_images_kernel(ImgJobs jobs, const float* __restrict__ wp, float* __restrict__ wimg) {
+  const ImgJob jb = jobs.j[blockIdx.x];
+  float* dst = wimg + (size_t)blockIdx.x * (kBlockImageBytes / 4);
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int nn = i >> 6, k = i & 63;
+    const float v = wp[jb.src_off + (size_t)(jb.n0 + nn) * jb.ldw + jb.k0 + k];
+    const float hi = tf32_rna(v);
+    const float lo = tf32_rna(v - hi);
+    const uint32_t off = sw128_offset(64, nn, k) >> 2;
+    dst[off] = hi;
+    dst[(kBlockHalfBytes >> 2) + off] = lo;
+  }
+}
+
+size_t tc_image_bytes() { return (size_t)kNumImages * kBlockImageBytes; }
+
+static int pack_images(const float* wp, float* wimg, cudaStream_t st) {
+  using P = WeightPack;
+  ImgJobs jobs;
+  int k = 0;
+  auto add = [&](int src, int ldw, int n0, int k0) { jobs.j[k++] = ImgJob{src, ldw, n0, k0}; };
+  add(P::f_a0, 64, 0, 0);
+  add(P::f_a1, 64, 0, 0);
+  for (int c = 0; c < 4; ++c) add(P::f_a2, 64, 64 * c, 0);
+  add(P::i_a0, 64, 0, 0);
+  add(P::i_a1, 64, 0, 0);
+  for (int c = 0; c < 4; ++c) {
+    add(P::i_a2, 64, 64 * c, 0);
+    add(P::i_a3, 256, 0, 64 * c);
+  }
+  add(P::s_a0a, 64, 0, 0);
+  add(P::s_a0b, 64, 0, 0);
+  add(P::s_a0c, 64, 0, 0);
+  add(P::s_a1, 64, 0, 0);
+  add(P::s_a2, 64, 0, 0);
+  for (int c = 0; c < 4; ++c) add(P::s_a3, 64, 64 * c, 0);
+  pack_images_kernel<<<kNumImages, 256, 0, st>>>(jobs, wp, wimg);
+  MOTIF_LAUNCHED("pack_images_kernel");
+  return 0;
+}
+
+__global__ void fill_ones_tc_kernel(float* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 1.0f;
+}
+
+int decode_tc(const motif_decode_t* a, cudaStream_t st) {
+  const motif_geom_t& g = a->geom;
+  DecodeScratch sc;
+  size_t need = 0;
+  decode_layout(g.B, g.N, g.H, g.W, g.HH, g.WW, &sc, (char*)a->workspace, &need);
+  if (a->workspace_bytes < need) return fail(MOTIF_E_WORKSPACE, "decode: workspace %zu < %zu bytes", a->workspace_bytes, need);
+  if (a->n_begin == a->n_end) return 0;
+  if (int rc = pack_weights(a, sc.wpack, st)) return rc;
+  if (int rc = pack_images(sc.wpack, sc.wimg, st)) return rc;
+  const int qs = g.HH * g.WW;
+  const int smem = (int)sizeof(TcSmem) + 1024;
+  static bool attr_done = false;
+  static int n_sm = 148;
+  if (!attr_done) {
+    MOTIF_CUDA(cudaFuncSetAttribute(imnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_splat_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(synth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0;
+    MOTIF_CUDA(cudaGetDevice(&dev));
+    MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  const int tiles128 = ceil_div(qs, 128), units256 = ceil_div(qs, 256);
+  const int grid128 = tiles128 < n_sm ? tiles128 : n_sm, grid256 = units256 < n_sm ? units256 : n_sm;
+  MOTIF_CUDA(cudaMemsetAsync(sc.acc_main, 0, sizeof(float) * (size_t)g.B * qs * 128, st));
+  MOTIF_CUDA(cudaMemsetAsync(sc.acc_side, 0, sizeof(float) * (size_t)g.B * qs * 4, st));
+  fill_ones_tc_kernel<<<148 * 8, 256, 0, st>>>(sc.acc_max, (size_t)g.B * qs);
+  MOTIF_LAUNCHED("fill_ones_tc_kernel");
+  for (int b = 0; b < g.B; ++b) {
+    {
+      ProfScope prof("imnet_tc_kernel", st);
+      imnet_tc_kernel<<<grid128, kTcThreads, smem, st>>>(g, g.B, b, a->feat, sc.wpack, sc.wimg, sc.imf);
+      MOTIF_LAUNCHED("imnet_tc_kernel");
+    }
+    for (int n = a->n_begin; n < a->n_end; ++n) {
+      const float t = a->target_t[b * g.N + n];
+      {
+        ProfScope prof("flow_splat_tc_kernel", st);
+        flow_splat_tc_kernel<<<grid128, kTcThreads, smem, st>>>(g, g.B, g.N, n, b, t, a->alpha, a->feat, a->flow_feat, sc.imf, sc.wpack, sc.wimg,
+                                                                 sc, a->flow_out);
+        MOTIF_LAUNCHED("flow_splat_tc_kernel");
+      }
+      {
+        ProfScope prof("synth_tc_kernel", st);
+        synth_tc_kernel<<<grid256, kTcThreads, smem, st>>>(g, g.B, g.N, n, b, t, a->residual, sc.wpack, sc.wimg, sc, a->rgb, a->dbg_synth_in);
+        MOTIF_LAUNCHED("synth_tc_kernel");
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace motif
