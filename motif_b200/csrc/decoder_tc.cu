@@ -136,22 +136,22 @@ struct EpiCtx {
   uint32_t ph_afree;
 };
 
-// sin(30 * pre) with pre folded:  v = pre * 30/(2 pi) (revolutions), reduced to [-0.5, 0.5], MUFU.SIN.
-// Absolute error ~1e-6 (fp32 rounding of v plus sin.approx), far below the TF32x3 accumulation noise x 30.
-constexpr float kRevPerUnit = 4.774648292756860f;  // 30 / (2 pi)
-__device__ __forceinline__ float sin_rev(float v) {
-  const float k = (v + 12582912.0f) - 12582912.0f;  // round to nearest integer (|v| < 2^22)
-  const float u = v - k;
-  return __sinf(u * 6.283185307179586f);
-}
+// sin(30 * pre): the epilogues form v = 30 * (D + bias) with one FFMA (constants are pre-scaled by 30) and
+// call sin.approx (one multiply by 1/(2 pi) + MUFU.SIN, which reduces the argument in fixed point).  For the
+// |v| < ~100 rad that occur here the absolute error is ~1e-6 rad-equivalent -- the same as the fp32 rounding
+// of v itself, and far below the 1e-3 output tolerance.
+constexpr float kRevPerUnit = 30.0f;  // SIREN omega (SIREN.py:45); name kept: "argument units per pre-activation unit"
+__device__ __forceinline__ float sin_rev(float v) { return __sinf(v); }
 
 __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const float h = tf32_rna(v[j]);
+    // hi rounded to TF32; lo = exact fp32 remainder (the tensor core truncates it to TF32: the dropped part
+    // is <= 2^-21 |v|)
+    const float h = tf32_round(v[j]);
     hi[j] = __float_as_uint(h);
-    lo[j] = __float_as_uint(tf32_rna(v[j] - h));
+    lo[j] = __float_as_uint(v[j] - h);
   }
   tmem_st16(taddr_hi, hi);
   tmem_st16(taddr_lo, lo);
@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom
       const int qy = qc / g.WW, qx = qc % g.WW;
       const Query qu = make_query(qy, qx, g);
       const size_t lr = (size_t)qu.iy * g.W + qu.ix;
+      if (lane == 0 && tile_id * 128 + (warp & 3) * 32 + 32 <= qs)  // this warp's 32 imnet rows: DRAM -> L2 ahead of the scatter
+        prefetch_l2(imf + ((size_t)rb * qs + tile_id * 128 + (warp & 3) * 32) * 64, 32 * 64 * 4);
       {
         float h[64];
         ldg_row64(flow_feat + ((size_t)rb * g.H * g.W + lr) * 64, h);
@@ -385,33 +387,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom
       }
       Footprint f = footprint(qx, qy, fx, fy);
       if (!live) f.finite = false;
-      for (int p = 0; p < 32; ++p) {
-        if (!__shfl_sync(0xffffffffu, (int)f.finite, p)) continue;
-        const int sx0 = __shfl_sync(0xffffffffu, f.x0, p), sy0 = __shfl_sync(0xffffffffu, f.y0, p);
-        const float se = __shfl_sync(0xffffffffu, e, p);
-        const int sq = __shfl_sync(0xffffffffu, q, p);
-        const size_t slr = __shfl_sync(0xffffffffu, (unsigned long long)lr, p);
-        const float sdx = __shfl_sync(0xffffffffu, dx, p), sdy = __shfl_sync(0xffffffffu, dy, p);
-        float w4[4];
+      // warp-cooperative scatter: one source pixel at a time, lanes 0-15 carry imnet(q) (64 ch), lanes 16-31 the
+      // nearest latent (64 ch); the source rows of 8 pixels are fetched together so their latencies overlap
+#pragma unroll 1
+      for (int p0 = 0; p0 < 32; p0 += 8) {
+        float4 vv[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) w4[k] = __shfl_sync(0xffffffffu, f.w[k], p);
-        const float* srow = lane < 16 ? imf + ((size_t)rb * qs + sq) * 64 + 4 * lane
-                                      : feat + ((size_t)rb * g.H * g.W + slr) * 64 + 4 * (lane - 16);
-        float4 v = __ldg(reinterpret_cast<const float4*>(srow));
-        v.x = __fmul_rn(v.x, se);
-        v.y = __fmul_rn(v.y, se);
-        v.z = __fmul_rn(v.z, se);
-        v.w = __fmul_rn(v.w, se);
-        const float edx = __fmul_rn(sdx, se), edy = __fmul_rn(sdy, se);
+        for (int j = 0; j < 8; ++j) {
+          const int p = p0 + j;
+          const int sq = __shfl_sync(0xffffffffu, qc, p);
+          const size_t slr = __shfl_sync(0xffffffffu, (unsigned long long)lr, p);
+          const float* srow = lane < 16 ? imf + ((size_t)rb * qs + sq) * 64 + 4 * lane
+                                        : feat + ((size_t)rb * g.H * g.W + slr) * 64 + 4 * (lane - 16);
+          vv[j] = __ldg(reinterpret_cast<const float4*>(srow));
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int cx = sx0 + (k & 1), cy = sy0 + (k >> 1);
-          if ((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH)) continue;
-          const size_t d = (size_t)b * qs + (size_t)cy * g.WW + cx;
-          const float wk = w4[k];
-          red_add_v4(sc.acc_main + d * 128 + 4 * lane, __fmul_rn(v.x, wk), __fmul_rn(v.y, wk), __fmul_rn(v.z, wk), __fmul_rn(v.w, wk));
-          if (lane == 0) red_add_v4(sc.acc_side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), __fmul_rn(se, wk), 1.0f);
-          if (lane == 1) red_max_nonneg(sc.acc_max + d, __fmul_rn(se, wk));
+        for (int j = 0; j < 8; ++j) {
+          const int p = p0 + j;
+          if (!__shfl_sync(0xffffffffu, (int)f.finite, p)) continue;
+          const int sx0 = __shfl_sync(0xffffffffu, f.x0, p), sy0 = __shfl_sync(0xffffffffu, f.y0, p);
+          const float se = __shfl_sync(0xffffffffu, e, p);
+          const float sdx = __shfl_sync(0xffffffffu, dx, p), sdy = __shfl_sync(0xffffffffu, dy, p);
+          float w4[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w4[k] = __shfl_sync(0xffffffffu, f.w[k], p);
+          float4 v = vv[j];
+          // softsplat_cp.py:332: tenInput * tenMetric.exp() is rounded before the kernel multiplies by the weight
+          v.x = __fmul_rn(v.x, se);
+          v.y = __fmul_rn(v.y, se);
+          v.z = __fmul_rn(v.z, se);
+          v.w = __fmul_rn(v.w, se);
+          const float edx = __fmul_rn(sdx, se), edy = __fmul_rn(sdy, se);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cx = sx0 + (k & 1), cy = sy0 + (k >> 1);
+            if ((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH)) continue;
+            const size_t d = (size_t)b * qs + (size_t)cy * g.WW + cx;
+            const float wk = w4[k];
+            red_add_v4(sc.acc_main + d * 128 + 4 * lane, __fmul_rn(v.x, wk), __fmul_rn(v.y, wk), __fmul_rn(v.z, wk), __fmul_rn(v.w, wk));
+            if (lane == 0) red_add_v4(sc.acc_side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), __fmul_rn(se, wk), 1.0f);
+            if (lane == 1) red_max_nonneg(sc.acc_max + d, __fmul_rn(se, wk));
+          }
         }
       }
     }
@@ -487,7 +503,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) synth_tc_kernel(motif_geom_t g,
       const float cnt = side.w;
       const float cnt_ = cnt == 0.0f ? 1.0f : cnt;
       const float wz_ = wz == 1.0f ? 0.0f : wz;
-      const float x_dx = __fdiv_rn(side.x, wz), x_dy = __fdiv_rn(side.y, wz);
+      // Ours.py:814 divides by warped_z; one IEEE reciprocal + multiplies is within 1 ulp of that per element
+      const float inv_wz = __fdiv_rn(1.0f, wz);
+      const float x_dx = side.x * inv_wz, x_dy = side.y * inv_wz;
+      {  // next unit's accumulator rows of this warp: DRAM -> L2 while this unit is being decoded
+        const int q_next = (unit + (int)gridDim.x) * 256 + c.tile * 128 + (warp & 3) * 32;
+        if (lane == 0 && q_next + 32 <= qs) {
+          prefetch_l2(sc.acc_main + ((size_t)b * qs + q_next) * 128, 32 * 128 * 4);
+          prefetch_l2(sc.acc_side + ((size_t)b * qs + q_next) * 4, 32 * 4 * 4);
+          prefetch_l2(sc.acc_max + ((size_t)b * qs + q_next), 32 * 4);
+        }
+      }
       const float x_cnt = __fdiv_rn(cnt, 16.0f), x_wz = __fdiv_rn(wz_, cnt_);
       float* dbg = (dbg_in && live) ? dbg_in + (size_t)bn * 198 * qs + q : nullptr;
       if (dbg) {
@@ -506,10 +532,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) synth_tc_kernel(motif_geom_t g,
 #pragma unroll
           for (int k4 = 0; k4 < 16; ++k4) {
             const float4 v = main_p[16 * kb + k4];
-            h[4 * k4 + 0] = __fdiv_rn(v.x, wz);
-            h[4 * k4 + 1] = __fdiv_rn(v.y, wz);
-            h[4 * k4 + 2] = __fdiv_rn(v.z, wz);
-            h[4 * k4 + 3] = __fdiv_rn(v.w, wz);
+            h[4 * k4 + 0] = v.x * inv_wz;
+            h[4 * k4 + 1] = v.y * inv_wz;
+            h[4 * k4 + 2] = v.z * inv_wz;
+            h[4 * k4 + 3] = v.w * inv_wz;
           }
           if (live) {
 #pragma unroll
@@ -651,10 +677,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) imnet_tc_kernel(motif_geom_t g,
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 320 + 64 * ch + c0 + 4 * j4);
-            hi[4 * j4 + 0] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 0], kRevPerUnit, bb.x))));
-            hi[4 * j4 + 1] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 1], kRevPerUnit, bb.y))));
-            hi[4 * j4 + 2] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 2], kRevPerUnit, bb.z))));
-            hi[4 * j4 + 3] = __float_as_uint(tf32_rna(sin_rev(fmaf(v[4 * j4 + 3], kRevPerUnit, bb.w))));
+            hi[4 * j4 + 0] = __float_as_uint(tf32_round(sin_rev(fmaf(v[4 * j4 + 0], kRevPerUnit, bb.x))));
+            hi[4 * j4 + 1] = __float_as_uint(tf32_round(sin_rev(fmaf(v[4 * j4 + 1], kRevPerUnit, bb.y))));
+            hi[4 * j4 + 2] = __float_as_uint(tf32_round(sin_rev(fmaf(v[4 * j4 + 2], kRevPerUnit, bb.z))));
+            hi[4 * j4 + 3] = __float_as_uint(tf32_round(sin_rev(fmaf(v[4 * j4 + 3], kRevPerUnit, bb.w))));
           }
           tmem_st16(c.lane_addr + kColD0 + c0, hi);
         }
