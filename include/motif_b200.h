@@ -152,6 +152,13 @@ int motif_decode(const motif_decode_t* args, void* stream);
 
 /* Self-test of the tcgen05 path on one tile: d[128][64] = x[128][64] * w[64][64]^T with `terms` = 1
  * (plain TF32) or 3 (error-compensated 3xTF32).  scratch: >= 32 KiB of device memory. */
+/* Tuning aid: install a device buffer of `capacity` (event id, clock64) pairs that CTA 0 of the tensor-core
+ * decoder kernels fills (NULL uninstalls).  Not used by the product path. */
+int motif_tc_set_trace(long long* buf, int capacity);
+/* Tuning aid: issue `reps` back-to-back tcgen05.mma kind::tf32 (M=128, N=n, K=8; A from TMEM or shared
+ * memory, round-robin over n_acc independent accumulators) in one CTA; out[0] = cycles to completion,
+ * out[1] = cycles spent issuing. */
+int motif_tc_mma_rate(long long* out, int n, int reps, int a_in_tmem, int n_acc, void* stream);
 int motif_tc_selftest(const float* x, const float* w, float* d, float* scratch, int terms, void* stream);
 
 #ifdef __cplusplus

@@ -33,6 +33,8 @@ EXPORTS = [
     "motif_decode_workspace_bytes",
     "motif_decode",
     "motif_tc_selftest",
+    "motif_tc_set_trace",
+    "motif_tc_mma_rate",
 ]
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3}
@@ -103,6 +105,10 @@ def _declare(lib):
     lib.motif_pack_latents.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_decode_workspace_bytes.restype = c_size_t
     lib.motif_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.motif_tc_set_trace.restype = c_int
+    lib.motif_tc_set_trace.argtypes = [c_void_p, c_int]
+    lib.motif_tc_mma_rate.restype = c_int
+    lib.motif_tc_mma_rate.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_tc_selftest.restype = c_int
     lib.motif_tc_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
     lib.motif_decode.restype = c_int

@@ -84,3 +84,5 @@ extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
     default: return fail(MOTIF_E_BADARG, "decode: unknown precision %d", args->precision);
   }
 }
+
+extern "C" int motif_tc_set_trace(long long* buf, int capacity) { return tc_set_trace(buf, capacity); }

@@ -100,5 +100,6 @@ int decode_simt(const motif_decode_t* a, cudaStream_t st);
 int decode_tc(const motif_decode_t* a, cudaStream_t st);
 int check_decode(const motif_decode_t* a);
 size_t tc_image_bytes();
+int tc_set_trace(long long* buf, int capacity);
 
 }  // namespace motif

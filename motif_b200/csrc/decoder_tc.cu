@@ -34,6 +34,22 @@ constexpr int kImgI = 6, kNumI = 10;     // imnet: a0, a1, (a2 chunk c, a3 k-blo
 constexpr int kImgS = 16, kNumS = 9;     // synth_net: a0a, a0b, a0c, a1, a2, a3 chunk 0..3
 constexpr int kNumImages = 25;
 
+// Optional pipeline trace (tests / tuning): CTA 0 records (event id, clock64) pairs of its tile-0 lane-0
+// epilogue thread and of the MMA issuer into a device buffer installed with motif_tc_set_trace().
+__device__ long long* g_trace = nullptr;
+__device__ int g_trace_cap = 0;
+__device__ int g_trace_n = 0;
+__device__ __forceinline__ void trace(int id) {
+  if (g_trace != nullptr && blockIdx.x == 0) {
+    const int i = atomicAdd(&g_trace_n, 1);
+    if (i < g_trace_cap) {
+      g_trace[2 * i] = id;
+      g_trace[2 * i + 1] = clock64();
+    }
+  }
+}
+#define TRACE_EPI(c, id) do { if ((c).tile == 0 && (threadIdx.x & 127) == 0) trace((id) + (c).tag); } while (0)
+
 struct Step {
   int dbuf;        // accumulator buffer: D0 (0) or D1 (1)
   bool a_new;      // the epilogue restaged the A operand for this step: wait a_ready
@@ -80,7 +96,7 @@ __device__ __forceinline__ void producer_loop(TcSmem& sm, const float* __restric
 // warp 1: MMA issuer (one thread)
 // ------------------------------------------------------------------------------------------------------
 template <int NSTEPS>
-__device__ __forceinline__ void issuer_loop(TcSmem& sm, const Step (&prog)[NSTEPS], int n_iters, uint32_t tmem_base) {
+__device__ __forceinline__ void issuer_loop(TcSmem& sm, const Step (&prog)[NSTEPS], int n_iters, uint32_t tmem_base, int tag) {
   const uint32_t idesc = idesc_tf32(128, 64);
   uint32_t g = 0;
   uint32_t ph_aready[2] = {0, 0};
@@ -96,6 +112,7 @@ __device__ __forceinline__ void issuer_loop(TcSmem& sm, const Step (&prog)[NSTEP
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
         const uint32_t tbase = tmem_base + tile * kTileCols;
+        if (tile == 0) trace(1000 + s + tag);
         if (st.a_new) {
           mbar_wait(&sm.bars.a_ready[tile], ph_aready[tile]);
           ph_aready[tile] ^= 1;
@@ -105,6 +122,7 @@ __device__ __forceinline__ void issuer_loop(TcSmem& sm, const Step (&prog)[NSTEP
           ph_dfree[tile][st.dbuf] ^= 1;
         }
         tc_fence_after();
+        if (tile == 0) trace(2000 + s + tag);
         const uint32_t dcol = tbase + kColD0 + 64 * st.dbuf;
         const uint32_t a_hi = tbase + (st.a_in_d0 ? kColD0 : kColAhi);
         bool acc = st.acc;
@@ -134,6 +152,7 @@ struct EpiCtx {
   uint32_t lane_addr;  // TMEM address of this thread's lane, column 0 of its tile
   uint32_t ph_dready[2];
   uint32_t ph_afree;
+  int tag;             // trace id offset of the kernel
 };
 
 // sin(30 * pre): the epilogues form v = 30 * (D + bias) with one FFMA (constants are pre-scaled by 30) and
@@ -161,12 +180,15 @@ __device__ __forceinline__ void publish_a(EpiCtx& c) {
   tmem_wait_st();
   tc_fence_before();
   mbar_arrive(&c.sm->bars.a_ready[c.tile]);
+  TRACE_EPI(c, 30);
 }
 
 __device__ __forceinline__ void wait_d(EpiCtx& c, int dbuf) {
+  TRACE_EPI(c, 10 + dbuf);
   mbar_wait(&c.sm->bars.d_ready[c.tile][dbuf], c.ph_dready[dbuf]);
   c.ph_dready[dbuf] ^= 1;
   tc_fence_after();
+  TRACE_EPI(c, 20 + dbuf);
 }
 __device__ __forceinline__ void release_d(EpiCtx& c, int dbuf) {
   tc_fence_before();
@@ -212,18 +234,19 @@ __device__ __forceinline__ void ldg_row64(const float* __restrict__ row, float (
 // Plain 64 -> 64 sine layer epilogue: D[dbuf] -> sin(30 (D + bias)) -> A.  `cb` = bias * 30/(2 pi) (smem).
 __device__ __forceinline__ void sine_epilogue(EpiCtx& c, int dbuf, const float* __restrict__ cb) {
   wait_d(c, dbuf);
-#pragma unroll 1
+  uint32_t r[64];
+  tmem_ld64(c.lane_addr + kColD0 + 64 * dbuf, r);
+  release_d(c, dbuf);
+#pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 16) {
     float v[16];
-    load16(c.lane_addr + kColD0 + 64 * dbuf + c0, v);
-    if (c0 == 48) release_d(c, dbuf);
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
       const float4 b = *reinterpret_cast<const float4*>(cb + c0 + 4 * j4);
-      v[4 * j4 + 0] = sin_rev(fmaf(v[4 * j4 + 0], kRevPerUnit, b.x));
-      v[4 * j4 + 1] = sin_rev(fmaf(v[4 * j4 + 1], kRevPerUnit, b.y));
-      v[4 * j4 + 2] = sin_rev(fmaf(v[4 * j4 + 2], kRevPerUnit, b.z));
-      v[4 * j4 + 3] = sin_rev(fmaf(v[4 * j4 + 3], kRevPerUnit, b.w));
+      v[4 * j4 + 0] = sin_rev(fmaf(__uint_as_float(r[c0 + 4 * j4 + 0]), kRevPerUnit, b.x));
+      v[4 * j4 + 1] = sin_rev(fmaf(__uint_as_float(r[c0 + 4 * j4 + 1]), kRevPerUnit, b.y));
+      v[4 * j4 + 2] = sin_rev(fmaf(__uint_as_float(r[c0 + 4 * j4 + 2]), kRevPerUnit, b.z));
+      v[4 * j4 + 3] = sin_rev(fmaf(__uint_as_float(r[c0 + 4 * j4 + 3]), kRevPerUnit, b.w));
     }
     split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
   }
@@ -234,20 +257,22 @@ __device__ __forceinline__ void sine_epilogue(EpiCtx& c, int dbuf, const float* 
 // cw[j] = (bias2_j * 30/2pi, w3[0][j], w3[1][j], w3[2][j]) for the 64 units of this chunk (smem).
 __device__ __forceinline__ void sine_out3_epilogue(EpiCtx& c, int dbuf, const float4* __restrict__ cw, float& o0, float& o1, float& o2) {
   wait_d(c, dbuf);
-#pragma unroll 1
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    float v[16];
-    load16(c.lane_addr + kColD0 + 64 * dbuf + c0, v);
-    if (c0 == 48) release_d(c, dbuf);
+  uint32_t r[64];
+  tmem_ld64(c.lane_addr + kColD0 + 64 * dbuf, r);
+  release_d(c, dbuf);
+  // four independent partial sums per output keep the FFMA chains short
+  float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 w = cw[c0 + j];
-      const float s = sin_rev(fmaf(v[j], kRevPerUnit, w.x));
-      o0 = fmaf(s, w.y, o0);
-      o1 = fmaf(s, w.z, o1);
-      o2 = fmaf(s, w.w, o2);
-    }
+  for (int j = 0; j < 64; ++j) {
+    const float4 w = cw[j];
+    const float s = sin_rev(fmaf(__uint_as_float(r[j]), kRevPerUnit, w.x));
+    p0[j & 3] = fmaf(s, w.y, p0[j & 3]);
+    p1[j & 3] = fmaf(s, w.z, p1[j & 3]);
+    p2[j & 3] = fmaf(s, w.w, p2[j & 3]);
   }
+  o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
+  o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+  o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
 }
 
 __device__ __forceinline__ void init_barriers(TcSmem& sm) {
@@ -282,7 +307,7 @@ __device__ __forceinline__ void tc_teardown(uint32_t tmem_base) {
   if ((threadIdx.x >> 5) == 2) tmem_dealloc<512>(tmem_base);
 }
 
-__device__ __forceinline__ EpiCtx make_epi(TcSmem& sm, uint32_t tmem_base) {
+__device__ __forceinline__ EpiCtx make_epi(TcSmem& sm, uint32_t tmem_base, int tag) {
   const int warp = threadIdx.x >> 5;
   EpiCtx c;
   c.sm = &sm;
@@ -290,6 +315,7 @@ __device__ __forceinline__ EpiCtx make_epi(TcSmem& sm, uint32_t tmem_base) {
   c.lane_addr = tmem_base + c.tile * kTileCols + ((uint32_t)((warp & 3) * 32) << 16);
   c.ph_dready[0] = c.ph_dready[1] = 0;
   c.ph_afree = 0;
+  c.tag = tag;
   return c;
 }
 __device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
@@ -333,9 +359,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom
   if (warp == 0) {
     if (lane == 0) producer_loop(sm, wimg, kImgF, kProgF, n_iters);
   } else if (warp == 1) {
-    if (lane == 0) issuer_loop(sm, kProgF, n_iters, tmem_base);
+    if (lane == 0) issuer_loop(sm, kProgF, n_iters, tmem_base, 100000);
   } else if (warp >= kEpiWarp0) {
-    EpiCtx c = make_epi(sm, tmem_base);
+    EpiCtx c = make_epi(sm, tmem_base, 100000);
     const int r = c.tile;  // reference frame
     const int rb = r * B + b;
     const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
@@ -357,17 +383,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom
       }
       // layer 0 epilogue: rank-1 terms of t (folded into c0), rel_y, rel_x
       wait_d(c, 0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        float v[16];
-        load16(c.lane_addr + kColD0 + c0, v);
-        if (c0 == 48) release_d(c, 0);
+      {
+        uint32_t r[64];
+        tmem_ld64(c.lane_addr + kColD0, r);
+        release_d(c, 0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 e = e0[c0 + j];
-          v[j] = sin_rev(fmaf(v[j], kRevPerUnit, fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, e.x))));
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 e = e0[c0 + j];
+            v[j] = sin_rev(fmaf(__uint_as_float(r[c0 + j]), kRevPerUnit, fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, e.x))));
+          }
+          split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
         }
-        split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
       }
       publish_a(c);
       sine_epilogue(c, 0, sm.consts + 256);
@@ -387,6 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom
       }
       Footprint f = footprint(qx, qy, fx, fy);
       if (!live) f.finite = false;
+      TRACE_EPI(c, 40);
       // warp-cooperative scatter: one source pixel at a time, lanes 0-15 carry imnet(q) (64 ch), lanes 16-31 the
       // nearest latent (64 ch); the source rows of 8 pixels are fetched together so their latencies overlap
 #pragma unroll 1
@@ -430,6 +460,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_splat_tc_kernel(motif_geom
           }
         }
       }
+      TRACE_EPI(c, 41);
     }
   }
   tc_teardown(tmem_base);
@@ -480,9 +511,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) synth_tc_kernel(motif_geom_t g,
   if (warp == 0) {
     if (lane == 0) producer_loop(sm, wimg, kImgS, kProgS, n_iters);
   } else if (warp == 1) {
-    if (lane == 0) issuer_loop(sm, kProgS, n_iters, tmem_base);
+    if (lane == 0) issuer_loop(sm, kProgS, n_iters, tmem_base, 200000);
   } else if (warp >= kEpiWarp0) {
-    EpiCtx c = make_epi(sm, tmem_base);
+    EpiCtx c = make_epi(sm, tmem_base, 200000);
     const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 640);
     const int bn = b * N + n;
@@ -558,24 +589,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) synth_tc_kernel(motif_geom_t g,
       }
       // layer 0 epilogue with the six rank-1 inputs
       wait_d(c, 0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        float v[16];
-        load16(c.lane_addr + kColD0 + c0, v);
-        if (c0 == 48) release_d(c, 0);
+      {
+        uint32_t r[64];
+        tmem_ld64(c.lane_addr + kColD0, r);
+        release_d(c, 0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 ea = e0[2 * (c0 + j)], eb = e0[2 * (c0 + j) + 1];
-          float pre = ea.x;
-          pre = fmaf(ea.y, x_dx, pre);
-          pre = fmaf(ea.z, x_dy, pre);
-          pre = fmaf(ea.w, zmax, pre);
-          pre = fmaf(eb.x, x_cnt, pre);
-          pre = fmaf(eb.y, x_wz, pre);
-          pre = fmaf(eb.z, t, pre);
-          v[j] = sin_rev(fmaf(v[j], kRevPerUnit, pre));
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 ea = e0[2 * (c0 + j)], eb = e0[2 * (c0 + j) + 1];
+            // two short chains instead of one 7-deep FFMA chain
+            const float pa = fmaf(ea.w, zmax, fmaf(ea.z, x_dy, fmaf(ea.y, x_dx, ea.x)));
+            const float pb = fmaf(eb.z, t, fmaf(eb.y, x_wz, eb.x * x_cnt));
+            v[j] = sin_rev(fmaf(__uint_as_float(r[c0 + j]), kRevPerUnit, pa + pb));
+          }
+          split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
         }
-        split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
       }
       publish_a(c);
       sine_epilogue(c, 0, sm.consts + 512);
@@ -634,9 +664,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) imnet_tc_kernel(motif_geom_t g,
   if (warp == 0) {
     if (lane == 0) producer_loop(sm, wimg, kImgI, kProgI, n_iters);
   } else if (warp == 1) {
-    if (lane == 0) issuer_loop(sm, kProgI, n_iters, tmem_base);
+    if (lane == 0) issuer_loop(sm, kProgI, n_iters, tmem_base, 0);
   } else if (warp >= kEpiWarp0) {
-    EpiCtx c = make_epi(sm, tmem_base);
+    EpiCtx c = make_epi(sm, tmem_base, 0);
     const int rb = c.tile * B + b;
     const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
     for (int it = 0; it < n_iters; ++it) {
@@ -651,17 +681,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) imnet_tc_kernel(motif_geom_t g,
         stage_row(c, h);
       }
       wait_d(c, 0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        float v[16];
-        load16(c.lane_addr + kColD0 + c0, v);
-        if (c0 == 48) release_d(c, 0);
+      {
+        uint32_t r[64];
+        tmem_ld64(c.lane_addr + kColD0, r);
+        release_d(c, 0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 e = e0[c0 + j];
-          v[j] = sin_rev(fmaf(v[j], kRevPerUnit, fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, e.x))));
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 e = e0[c0 + j];
+            v[j] = sin_rev(fmaf(__uint_as_float(r[c0 + j]), kRevPerUnit, fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, e.x))));
+          }
+          split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
         }
-        split_store16(c.lane_addr + kColAhi + c0, c.lane_addr + kColAlo + c0, v);
       }
       publish_a(c);
       sine_epilogue(c, 0, sm.consts + 256);
@@ -733,6 +766,14 @@ __global__ void pack_images_kernel(ImgJobs jobs, const float* __restrict__ wp, f
 }
 
 size_t tc_image_bytes() { return (size_t)kNumImages * kBlockImageBytes; }
+
+int tc_set_trace(long long* buf, int capacity) {
+  int zero = 0;
+  MOTIF_CUDA(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+  MOTIF_CUDA(cudaMemcpyToSymbol(g_trace_cap, &capacity, sizeof(int)));
+  MOTIF_CUDA(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(int)));
+  return 0;
+}
 
 static int pack_images(const float* wp, float* wimg, cudaStream_t st) {
   using P = WeightPack;

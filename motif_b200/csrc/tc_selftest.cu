@@ -92,9 +92,78 @@ __global__ void __launch_bounds__(192, 1) tc_selftest_kernel(const float* __rest
   if (warp == 1) tmem_dealloc<256>(tmem);
 }
 
+// MMA issue-rate probe: `reps` back-to-back tcgen05.mma (M = 128, N = n, K = 8, A from TMEM or smem) on garbage
+// operands; out[0] = cycles from first issue to commit completion, out[1] = cycles spent issuing.
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(long long* out, int n, int reps, int a_in_tmem, int n_acc) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * 65536);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * 65536 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.0f;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp == 0 && lane == 0) {
+    const uint32_t idesc = idesc_tf32(128, n);
+    const uint32_t b0 = smem_u32(smem), a0 = smem_u32(smem) + 65536;
+    uint64_t bdesc[4], adesc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bdesc[j] = smem_desc_sw128(b0 + j * 32);
+      adesc[j] = smem_desc_sw128(a0 + j * 32);
+    }
+    const uint32_t d0 = tmem + 256, d1 = tmem + 256 + ((n_acc > 1) ? n : 0);
+    const long long t0 = clock64();
+    // 8 MMAs per trip with loop-invariant descriptors; accumulators alternate when n_acc == 2
+    for (int i = 0; i < reps; i += 8) {
+      const uint32_t accf = i > 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dcol = (j & 1) ? d1 : d0;
+        const uint32_t acc = (j < 2) ? accf : 1u;
+        if (a_in_tmem) {
+          mma_tf32_ts(dcol, tmem + j * 8, bdesc[j & 3], idesc, acc);
+        } else {
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "setp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(dcol),
+              "l"(adesc[j & 3]), "l"(bdesc[j & 3]), "r"(idesc), "r"(acc)
+              : "memory");
+        }
+      }
+    }
+    const long long t1 = clock64();
+    mma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0;
+    out[1] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace motif
 
 using namespace motif;
+
+extern "C" int motif_tc_mma_rate(long long* out, int n, int reps, int a_in_tmem, int n_acc, void* stream) {
+  MOTIF_REQUIRE(out && n >= 16 && n <= 256 && n % 16 == 0 && reps > 0 && n_acc >= 1 && n_acc <= 2 && n_acc * n <= 256 && reps % 8 == 0, "tc_mma_rate: bad argument");
+  const int smem = 2 * 65536 + 1024;
+  MOTIF_CUDA(cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  tc_mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, n, reps, a_in_tmem, n_acc);
+  MOTIF_LAUNCHED("tc_mma_rate_kernel");
+  return 0;
+}
 
 // x [128][64], w [64][64] ([out][in], row-major), d [128][64] = x * w^T; scratch >= 32 KB device memory.
 extern "C" int motif_tc_selftest(const float* x, const float* w, float* d, float* scratch, int terms, void* stream) {
