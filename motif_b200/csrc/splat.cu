@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restr
     const float m = metric_scale<MODE>(metric, p);
     const float* src = in + (size_t)b * c * hw + s;
     float* o = out + (size_t)b * c_out * hw;
+#pragma unroll 8
     for (int ch = 0; ch < c; ++ch) {
       float v = src[(size_t)ch * hw];
       if (MODE >= MOTIF_SPLAT_LINEAR) v = __fmul_rn(v, m);
@@ -154,7 +155,33 @@ __device__ __forceinline__ void cswap(int& sa, float& wa, int& sb, float& wb) {
 
 // ------------------------------------------------------------------------------------------------
 // Destination-centric pass 2: one thread per destination pixel, all channels.
+// The channel loop is specialised on the largest contribution count of the warp (K = 4, 6 or 8 slots), so a
+// warp whose destinations all have <= 4 contributions (the common case for smooth flows) executes 4 gathers
+// and 4 multiply-adds per pixel-channel and nothing else.
 // ------------------------------------------------------------------------------------------------
+template <int MODE, int K>
+__device__ __forceinline__ void gather_channels(const float* __restrict__ plane, float* __restrict__ optr, int c, size_t hw, int cnt,
+                                                const unsigned (&src)[kBinSlots], const float (&wt)[kBinSlots], const float (&m)[kBinSlots],
+                                                bool store) {
+#pragma unroll 4
+  for (int ch = 0; ch < c; ++ch) {
+    float v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = __ldg(plane + src[k]);  // dead slots read element 0 (weight 0, not accumulated)
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float t = v[k];
+      if (MODE >= MOTIF_SPLAT_LINEAR) t = __fmul_rn(t, m[k]);
+      t = __fmul_rn(t, wt[k]);
+      if (k < cnt) acc = __fadd_rn(acc, t);
+    }
+    if (store) *optr = acc;
+    plane += hw;
+    optr += hw;
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metric,
                                                            float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
@@ -163,20 +190,20 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restri
   const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
   const int b = blockIdx.y;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= hw) return;
-  const size_t gd = (size_t)b * hw + d;
-  const int cnt = min(ws.count[gd], kBinSlots);
-  int src[kBinSlots];
+  const bool live = d < hw;
+  const size_t gd = (size_t)b * hw + (live ? d : 0);
+  const int cnt = live ? min(ws.count[gd], kBinSlots) : 0;
+  int srci[kBinSlots];
   float wt[kBinSlots];
 #pragma unroll
   for (int k = 0; k < kBinSlots; ++k) {
-    const bool live = k < cnt;
-    src[k] = live ? ws.ent_src[(size_t)k * total + gd] : 0x7fffffff;
-    wt[k] = live ? ws.ent_w[(size_t)k * total + gd] : 0.0f;
+    const bool on = k < cnt;
+    srci[k] = on ? ws.ent_src[(size_t)k * total + gd] : 0x7fffffff;
+    wt[k] = on ? ws.ent_w[(size_t)k * total + gd] : 0.0f;
   }
   // sort by source index (Batcher odd-even merge network for 8 keys): the accumulation order becomes
   // source raster order whatever order the binning atomics handed the slots out in.
-#define CS(a, b) cswap(src[a], wt[a], src[b], wt[b])
+#define CS(a, b) cswap(srci[a], wt[a], srci[b], wt[b])
   CS(0, 1); CS(2, 3); CS(4, 5); CS(6, 7);
   CS(0, 2); CS(1, 3); CS(4, 6); CS(5, 7);
   CS(1, 2); CS(5, 6);
@@ -184,38 +211,26 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restri
   CS(2, 4); CS(3, 5);
   CS(1, 2); CS(3, 4); CS(5, 6);
 #undef CS
+  unsigned src[kBinSlots];
   float m[kBinSlots];
 #pragma unroll
   for (int k = 0; k < kBinSlots; ++k) {
+    src[k] = (k < cnt) ? (unsigned)srci[k] : 0u;
     m[k] = 1.0f;
     if (MODE >= MOTIF_SPLAT_LINEAR && k < cnt) m[k] = metric_scale<MODE>(metric, (size_t)b * hw + src[k]);
-    if (k >= cnt) src[k] = 0;
   }
-  const float* ib = in + (size_t)b * c * hw;
-  float* ob = out + (size_t)b * c_out * hw + d;
-#pragma unroll 2
-  for (int ch = 0; ch < c; ++ch) {
-    const float* plane = ib + (size_t)ch * hw;
-    float v[kBinSlots];
-#pragma unroll
-    for (int k = 0; k < kBinSlots; ++k) v[k] = (k < cnt) ? __ldg(plane + src[k]) : 0.0f;
-    float acc = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kBinSlots; ++k) {
-      if (k < cnt) {
-        float t = v[k];
-        if (MODE >= MOTIF_SPLAT_LINEAR) t = __fmul_rn(t, m[k]);
-        acc = __fadd_rn(acc, __fmul_rn(t, wt[k]));
-      }
-    }
-    ob[(size_t)ch * hw] = acc;
-  }
-  if (MODE != MOTIF_SPLAT_SUMMATION) {
+  const int wmax = __reduce_max_sync(0xffffffffu, cnt);
+  const float* plane = in + (size_t)b * c * hw;
+  float* optr = out + (size_t)b * c_out * hw + (live ? d : 0);
+  if (wmax <= 4) gather_channels<MODE, 4>(plane, optr, c, hw, cnt, src, wt, m, live);
+  else if (wmax <= 6) gather_channels<MODE, 6>(plane, optr, c, hw, cnt, src, wt, m, live);
+  else gather_channels<MODE, 8>(plane, optr, c, hw, cnt, src, wt, m, live);
+  if (MODE != MOTIF_SPLAT_SUMMATION && live) {
     float acc = 0.0f;
 #pragma unroll
     for (int k = 0; k < kBinSlots; ++k)
       if (k < cnt) acc = __fadd_rn(acc, __fmul_rn(m[k], wt[k]));
-    ob[(size_t)c * hw] = acc;
+    optr[(size_t)c * hw] = acc;
   }
 }
 

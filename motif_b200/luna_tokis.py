@@ -1,0 +1,117 @@
+"""Bind the sm_100a decoder into a reference ``LunaTokis`` instance (``models/modules/Ours.py``).
+
+    from models.modules.Ours import LunaTokis          # the user's reference checkout
+    import motif_b200.luna_tokis as mb
+    model = LunaTokis(setting=5); model.load_state_dict(torch.load("best.pth"))   # unchanged
+    mb.install(model)                                   # forward() now runs the B200 hot path
+
+``install`` keeps the module tree (and therefore the ``state_dict`` layout ``best.pth`` needs) and
+replaces ``forward`` by ``forward_b200``, which
+
+* runs the surround exactly as the reference does, through the instance's own sub-modules
+  (RAFT on the four frame pairs, the psi reliability maps, ``ZSM_encoder``, ``flow_process``;
+  ``Ours.py:512-638``) -- glue re-stated here because the reference's ``forward`` is monolithic;
+* hands the three LR latents to ``SpaceTimeDecoder`` (``Ours.py:659-858`` on sm_100a) and returns the
+  reference's triple ``(clamp(out) [N,B,3,HH,WW], flow / 20 / (HH/H), flow_GT)`` (``Ours.py:858``).
+
+Also swaps the three splat modules (``self.fwarp*``) for the motif_b200 operators, so any other
+caller of them inside the model goes through the same library.
+
+Inference only (``use_GT=False``, ``eval()``; the reference's ``test()`` path,
+``VideoSR_base_model.py:169-195``); training-time teacher forcing raises.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+import torch.nn.functional as F
+from torch.nn.functional import interpolate
+
+from .decoder import SpaceTimeDecoder, hr_size_from_scale
+from .softsplat_count_cp import Softsplat_Count
+from .softsplat_cp import Softsplat
+from .softsplat_max_cp import Softsplat_Max
+
+
+def surround(self, x, target_t, scale, iter=12):
+    """``Ours.py:512-638``: everything before the hot path.  Returns
+    ``(feat [2B,64,H,W], flow_feat [2B,64,H,W], residual [B,64,H,W], target_t [B,N], (HH, WW))``."""
+    x = x.permute(0, 2, 1, 3, 4)
+    x = x[:, :, x.shape[2] // 2 - 1:x.shape[2] // 2 + 1]
+    with torch.no_grad():
+        target_t = torch.stack(target_t, 1).squeeze(-1)
+        B, N = target_t.shape
+        B, _, _, H, W = x.shape
+        HH, WW = hr_size_from_scale(H, W, scale)
+
+        # HR input motion from the pretrained RAFT on the pairs 00, 01, 10, 11 (Ours.py:540-555)
+        x_norm = interpolate(x.reshape(B, -1, H, W), size=(HH, WW), mode="bilinear", align_corners=False).reshape(B, -1, 2, HH, WW)
+        fr0, fr1 = x_norm[:, :, 0], x_norm[:, :, 1]
+        flow = self.flow_predictor(torch.cat([fr0, fr0, fr1, fr1], dim=0) * 255.0, torch.cat([fr0, fr1, fr0, fr1], dim=0) * 255.0, iters=iter)[-1]
+        fr0, fr1 = x[:, :, 0], x[:, :, 1]
+        flow = interpolate(flow, size=(H, W), mode="bilinear", align_corners=False) * (H / HH)
+        flow = flow.reshape(4, B, 2, H, W)
+        flow[0] *= 0.0
+        flow[3] *= 0.0
+        flow = flow.reshape(4 * B, 2, H, W)
+
+        # reliability maps psi_photo, psi_flow, psi_var (Ours.py:562-578)
+        warped, _ = self.bwarp(torch.cat([fr0, fr1, fr0, fr1], dim=0), flow)
+        psi_photo = F.l1_loss(input=torch.cat([fr0, fr0, fr1, fr1], dim=0), target=warped, reduction="none").mean(1)
+        flow = flow.reshape(4, B, 2, H, W)
+        warped, _ = self.bwarp(-torch.cat([flow[0], flow[2], flow[1], flow[3]], dim=0), flow.reshape(4 * B, 2, H, W))
+        psi_flow = F.l1_loss(input=flow.reshape(4 * B, 2, H, W), target=warped, reduction="none").mean(1)
+        f = flow.reshape(4 * B, -1, H, W)
+        sq_mean, mean_sq = torch.split(
+            F.conv3d(F.pad(torch.cat([f ** 2, f], 1), (1, 1, 1, 1), mode="reflect").unsqueeze(1), self.g_filter).squeeze(1), 2, dim=1)
+        psi_var = (sq_mean - mean_sq ** 2).clip(1e-9, None).sqrt().mean(1)
+        psies = torch.stack([psi_photo, psi_flow / 10.0, psi_var], dim=1)
+
+    # encoder features (Ours.py:601-611)
+    feat = self.encoder(torch.stack([fr0, fr1], 1), None)
+    residual = feat[:, feat.shape[1] // 2].reshape(B, -1, H, W)
+    feat = torch.cat((feat[:, feat.shape[1] // 2 - 1], feat[:, feat.shape[1] // 2 + 1]), 0)
+
+    # flow encoder input: [flow / 20, psies, ref_start_durations / 8] (Ours.py:613-638, trans=False, input_Z=True)
+    flow = flow.reshape(4 * B, 2, H, W)
+    durations = torch.tensor([[0, 0], [0, 8], [8, 0], [8, 8]], dtype=torch.float32, device=flow.device).unsqueeze(1)
+    flow_feat = torch.cat(
+        (
+            (flow / 20.0).reshape(2, 2, B, -1, H, W).permute(0, 2, 1, 3, 4, 5).reshape(2 * B, 2, -1, H, W),
+            psies.reshape(2, 2, B, -1, H, W).permute(0, 2, 1, 3, 4, 5).reshape(2 * B, 2, -1, H, W),
+            durations.reshape(2, 4, 1, 1).unsqueeze(1).repeat(1, B, 1, H, W).reshape(2 * B, 2, 2, H, W) / 8.0,
+        ),
+        dim=2,
+    ).reshape(2 * B, -1, H, W)
+    flow_feat = self.flow_process(flow_feat)
+    return feat, flow_feat, residual, target_t, (HH, WW)
+
+
+def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, train_idx=0, use_GT=True, iter=12, flows=None):
+    """Same signature and return value as ``LunaTokis.forward`` (``Ours.py:512, 858``)."""
+    if self.training or use_GT:
+        raise NotImplementedError("motif_b200 implements the inference path (eval(), use_GT=False), as VideoSRBaseModel.test() calls it")
+    for flag, want in (("local_ensemble", False), ("res_liff", False), ("siren", True), ("trans", False), ("warp_to_many", False)):
+        if getattr(self, flag, want) != want:
+            raise NotImplementedError(f"motif_b200 decodes the shipped configuration (setting 5); {flag}={getattr(self, flag)} is not supported")
+    with torch.no_grad():
+        feat, flow_feat, residual, tt, (HH, WW) = surround(self, x, target_t, scale, iter)
+        dec = getattr(self, "_motif_decoder", None)
+        sd_version = sum(p._version for p in self.parameters())
+        if dec is None or dec.device != feat.device or self._motif_decoder_version != sd_version:
+            dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, precision=getattr(self, "_motif_precision", "tf32x3"))
+            object.__setattr__(self, "_motif_decoder", dec)
+            object.__setattr__(self, "_motif_decoder_version", sd_version)
+        rgb, flow_out = dec.decode(feat.float(), flow_feat.float(), residual.float(), tt, (HH, WW))
+    return rgb, flow_out, 0.0  # Ours.py:580, 858: flow_GT = 0 on the inference path, returned as (0 / 20.0) / (HH / H)
+
+
+def install(model, precision: str = "tf32x3"):
+    """Patch a reference ``LunaTokis`` instance in place and return it."""
+    object.__setattr__(model, "_motif_precision", precision)
+    model.fwarp = Softsplat()
+    model.fwarp_max = Softsplat_Max()
+    model.fwarp_count = Softsplat_Count()
+    model.forward = types.MethodType(forward_b200, model)
+    return model

@@ -77,3 +77,41 @@ def _worker(rank, world, port, n_ts):
 @pytest.mark.parametrize("n_ts", [7, 1])
 def test_two_rank_gloo_broadcast_and_gather(n_ts):
     mp.spawn(_worker, args=(2, _free_port(), n_ts), nprocs=2, join=True)
+
+
+def test_luna_tokis_surround_matches_reference_forward():
+    """CPU, build container only: the re-stated surround glue (Ours.py:512-638) reproduces, bit for bit, the
+    hot-path inputs of the unmodified reference forward (captured with hooks)."""
+    from oracle import ref_shims
+
+    if not ref_shims.reference_available():
+        pytest.skip("reference checkout absent (GPU box)")
+    from motif_b200 import luna_tokis
+
+    model = ref_shims.build_reference_model(seed=0)
+    torch.manual_seed(3)
+    x = torch.rand(1, 2, 3, 32, 48)
+    target_t = [torch.tensor([[0.25]]), torch.tensor([[0.75]])]
+    ref = ref_shims.run_reference_forward(model, x, target_t, 4)
+    with torch.no_grad(), ref_shims.cpu_cuda_aliases():
+        feat, flow_feat, residual, tt, hr = luna_tokis.surround(model, x, target_t, 4, iter=4)
+    assert hr == (128, 192) and tuple(tt.shape) == (1, 2)
+    assert torch.equal(feat, ref["feat"])
+    assert torch.equal(residual, ref["residual"])
+    assert torch.equal(flow_feat, ref["flow_feat"])
+
+
+def test_install_keeps_state_dict_layout_and_refuses_training():
+    from oracle import ref_shims
+
+    if not ref_shims.reference_available():
+        pytest.skip("reference checkout absent (GPU box)")
+    from motif_b200 import luna_tokis
+
+    model = ref_shims.build_reference_model(seed=0)
+    keys = list(model.state_dict().keys())
+    luna_tokis.install(model)
+    assert list(model.state_dict().keys()) == keys  # best.pth still loads with strict=True
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(torch.rand(1, 2, 3, 32, 48), None, [torch.tensor([[0.5]])], 4, use_GT=False)
