@@ -129,11 +129,11 @@ CPU_SAMPLE_NOTE = "Adobe240 workload cropped to LR 45x80 -> 180x320, all 7 times
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="motif", choices=["motif", "reference"])
     ap.add_argument("--workload", default="adobe240_x4_t8")
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "fp32"])
+    ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -147,7 +147,7 @@ def main():
     B, N = 1, len(times)
     qs = HH * WW
     config = {"workload": f"{args.workload}: LR {H}x{W} -> HR {HH}x{WW}, {N} timestamps, B=1, synthetic latents + synthetic best.pth-layout weights",
-              "l2": "per-step working set (imnet features 472 MB + splat accumulators 491 MB) >> 126 MB L2; no explicit flush",
+              "l2": "per-step working set (per-source rows 472 MB + destination lists 118 MB + frames 77 MB) >> 126 MB L2; no explicit flush",
               "parallelism": f"timestamps sharded over {world} rank(s), NCCL broadcast of LR latents per step" if world > 1 else "single GPU"}
 
     if args.impl == "reference":
@@ -231,7 +231,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    kernel_names = ["imnet_kernel", "flow_splat_kernel", "synth_kernel", "imnet_tc_kernel", "flow_splat_tc_kernel", "synth_tc_kernel"]
+    kernel_names = ["imnet_kernel", "flow_splat_kernel", "synth_kernel", "imnet_tc_kernel", "flow_splat_tc_kernel", "synth_tc_kernel",
+                    "imnet_f16_kernel", "flow_bin_f16_kernel", "synth_f16_kernel"]
     ms, launches = timed(False, args.steps, profile=True)
     prof = _lib.prof_collect(kernel_names)
     _lib.prof_enable(False)
@@ -258,9 +259,16 @@ def main():
         "imnet_kernel": FLOP_IMNET_ROW * 2 * B * qs, "imnet_tc_kernel": FLOP_IMNET_ROW * 2 * B * qs,
         "flow_splat_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "flow_splat_tc_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs,
         "synth_kernel": FLOP_SYNTH_ROW * qs, "synth_tc_kernel": FLOP_SYNTH_ROW * qs,
+        "imnet_f16_kernel": FLOP_IMNET_ROW * 2 * B * qs, "flow_bin_f16_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "synth_f16_kernel": FLOP_SYNTH_ROW * qs,
     }
     live = {k: v for k, v in prof.items() if v[1] > 0}
-    tf32_peak = peaks["bf16_sustained"] / 2.0
+    # tensor peak of the operand type the MMAs run in: kind::f16 = the measured bf16/fp16 dense figure,
+    # kind::tf32 = half of it.  Algorithmic FLOPs count every MAC of the reference ONCE: the three split-product
+    # passes are not counted, so an error-compensated path cannot exceed 1/3 of this peak by construction.
+    if args.precision == "f16x3":
+        tensor_peak, peak_name = peaks["bf16_sustained"], "fp16 dense = bf16 sustained"
+    else:
+        tensor_peak, peak_name = peaks["bf16_sustained"] / 2.0, "TF32 dense = 0.5 x bf16 sustained"
     kernels = {}
     for k, (tot_ms, cnt) in live.items():
         avg = tot_ms / cnt
@@ -270,8 +278,10 @@ def main():
     if live:
         dom = max(live, key=lambda k: live[k][0])
         a = kernels[dom]["tflops"]
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": a, "peak": tf32_peak, "unit": "TFLOP/s", "frac": a / tf32_peak, "traffic": None,
-                    "peak_note": f"TF32 dense = 0.5 x bf16 sustained, {peaks['source']}; algorithmic FLOPs (K un-padded, one pass counted)"}
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": a, "peak": tensor_peak, "unit": "TFLOP/s", "frac": a / tensor_peak, "traffic": None,
+                    "peak_note": f"{peak_name}, {peaks['source']}; algorithmic FLOPs (K un-padded, one pass counted; 3 split-product passes run)"}
+        step_flops = (2 * FLOP_FLOW_IMNET_ROW + FLOP_SYNTH_ROW) * N * qs + FLOP_IMNET_ROW * 2 * B * qs
+        roofline["whole_step_tflops"] = step_flops * args.steps / (ms * 1e-3) / 1e12
 
     # ---- HBM roofline of the stand-alone softmax splat operator (C=130, one 720x1280 reference frame) ----
     torch.manual_seed(0)
@@ -310,7 +320,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "tf32x3 (fp32-equivalent)" if args.precision == "tf32x3" else "f32", "data": "synthetic", "config": config,
+        "dtype": {"f16x3": "f16x3 (two-piece fp16 split, fp32 accumulate; fp32-equivalent)", "tf32x3": "tf32x3 (fp32-equivalent)", "fp32": "f32"}[args.precision],
+        "data": "synthetic", "config": config,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MOTIF_ABI_VERSION 1
+#define MOTIF_ABI_VERSION 2
 
 #define MOTIF_E_BADARG (-1)   /* null pointer, non-positive size, unknown mode        */
 #define MOTIF_E_WORKSPACE (-2) /* workspace smaller than the *_workspace_bytes() answer */
@@ -136,14 +136,17 @@ typedef struct {
   size_t workspace_bytes;
   /* optional debug taps (may be NULL), NCHW like the reference tensors:
    *   dbg_splat [B*N, 133, HH, WW] = blended splat (130) + extra (3)  (Ours.py:810-836) */
-  float* dbg_synth_in; /* [B*N, 198, HH, WW] the synth_net input (Ours.py:839-844) */
+  float* dbg_synth_in; /* [B*N, 198, HH, WW] the synth_net input (Ours.py:839-844); fp32 / tf32x3 only */
+  float* dbg_pre0;     /* [B*N, 64, HH, WW] synth_net layer-0 pre-activation (synth_in * W0^T + b0); f16x3 only */
   int n_begin, n_end;  /* timestamps [n_begin, n_end) of each clip are decoded (sharding) */
   int precision;       /* MOTIF_PRECISION_*: arithmetic of the three SIREN MLPs               */
 } motif_decode_t;
 
-/* MLP arithmetic.  TF32X3: tcgen05 tensor cores, error-compensated 3xTF32 (fp32-equivalent
- * products, fp32 TMEM accumulation).  FP32: CUDA-core FFMA + sinf, the numerical yardstick. */
-enum { MOTIF_PRECISION_TF32X3 = 0, MOTIF_PRECISION_FP32 = 1 };
+/* MLP arithmetic.  F16X3 (default of the Python mirror): tcgen05 kind::f16, every fp32 operand split into two
+ * fp16 pieces (22 significant bits) and three products per term, fp32 TMEM accumulation; layer 0 of each MLP
+ * evaluated per LR pixel; list-based (atomic-free) splat.  TF32X3: first-generation tensor-core path,
+ * error-compensated 3xTF32 with a float-atomic scatter.  FP32: CUDA-core FFMA + sinf, the numerical yardstick. */
+enum { MOTIF_PRECISION_TF32X3 = 0, MOTIF_PRECISION_FP32 = 1, MOTIF_PRECISION_F16X3 = 2 };
 
 size_t motif_decode_workspace_bytes(int B, int N, int H, int W, int HH, int WW);
 /* Whole hot path for one batch of clips from resident LR latents: imnet once per clip, then

@@ -70,6 +70,7 @@ class DecodeT(Structure):
         ("rgb", c_void_p), ("flow_out", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("dbg_synth_in", c_void_p),
+        ("dbg_pre0", c_void_p),
         ("n_begin", c_int), ("n_end", c_int),
         ("precision", c_int),
     ]

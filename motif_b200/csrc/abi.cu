@@ -81,6 +81,7 @@ extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
   switch (args->precision) {
     case MOTIF_PRECISION_TF32X3: return decode_tc(args, (cudaStream_t)stream);
     case MOTIF_PRECISION_FP32: return decode_simt(args, (cudaStream_t)stream);
+    case MOTIF_PRECISION_F16X3: return decode_f16(args, (cudaStream_t)stream);
     default: return fail(MOTIF_E_BADARG, "decode: unknown precision %d", args->precision);
   }
 }

@@ -1,0 +1,968 @@
+// Space-time local implicit decoder, second generation (precision "f16x3"): the three SIREN MLPs of
+// Ours.py:470-471, 487-491 on tcgen05.mma kind::f16 with fp32 accumulators in tensor memory.
+//
+// What changed against decoder_tc.cu (kept as precision "tf32x3"), each step evidenced in DESIGN.md section 4:
+//  * Arithmetic: every fp32 operand is split into TWO fp16 pieces (hi = round-to-fp16, lo = fp16 of the exact
+//    remainder; 22 significant bits, the same as the hi/lo TF32 split) and products are formed as
+//    A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.  A kind::f16 instruction (K = 16) costs the same tensor-pipe cycles as a
+//    kind::tf32 one (K = 8) (profiles/r1_probe_mma_rates.txt), so the MLPs need half the tensor time of 3xTF32.
+//    Weights are scaled per layer by a power of two into the fp16 normal range (exact), activations are sines.
+//  * Layer 0 of each MLP is linear in a nearest-latent row, so its 64-column blocks are evaluated ONCE PER LR PIXEL
+//    (lr_tables_kernel, exact fp32) and the per-query work is a table row plus the rank-1 coordinate terms.
+//  * The forward splat is linear, so synth_net layer 0 commutes with it: imnet's output layer is composed with
+//    synth_net's first 64 columns (W0a * W3), the nearest-feature block (W0b) is added per source, and ONE
+//    64-channel row Y per source pixel is splatted instead of 128 channels; layer 0 of synth_net needs no MMA.
+//  * The splat itself is destination-centric: flow_bin_kernel appends (source id, e*w) to a 16-slot list of every
+//    destination it covers (one int atomic per corner instead of 33 float4 atomics), synth_kernel gathers the
+//    listed rows with coalesced loads.  Lists that overflow fall back to float atomics on a spill accumulator.
+//  * All weight blocks of a kernel stay resident in shared memory (no per-tile weight streaming).
+//
+// One persistent CTA per SM, 12 warps: warp 0 loads the weight images once, warp 1 (one thread) issues every MMA,
+// warp 2 owns the TMEM allocation, warps 4-7 / 8-11 are the two 128-pixel tiles in flight (thread == pixel row ==
+// TMEM lane).  Per tile the 256 TMEM columns are [0,32) A_hi [32,64) A_lo [64,96) A2_hi [96,128) A2_lo
+// [128,192) D0 [192,256) D1 (fp16 pairs per A column).
+#include <cuda_fp16.h>
+
+#include "decoder_common.cuh"
+#include "tc_common.cuh"
+
+namespace motif {
+namespace f16 {
+
+using namespace tc;
+
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kTileCols = 256;
+constexpr uint32_t kColA = 0, kColA2 = 64, kColD0 = 128;
+constexpr int kSlots = 16;                 // list entries per destination pixel
+constexpr int kBlkHalf = 64 * 64 * 2;      // one fp16 64x64 block (hi or lo)
+constexpr int kBlkBytes = 2 * kBlkHalf;    // hi image followed by lo image
+constexpr float kOmega = 30.0f;            // SIREN.py:45
+
+// weight block images (program order per kernel) and per-layer scale slots
+enum { kImgF1 = 0, kImgF2 = 1, kImgI1 = 5, kImgI2 = 6, kImgI3 = 10, kImgS1 = 14, kImgS2 = 15, kImgS3 = 16, kNumImg = 20 };
+enum { kScF1 = 0, kScF2, kScI1, kScI2, kScI3, kScS1, kScS2, kScS3, kNumSc };
+
+struct Scratch {
+  float* wpack;             // WeightPack (fp32, checkpoint values regrouped)
+  float* fold;              // [64][256] W0a*W3 then [64] W0a*b3
+  float* scales;            // [kNumSc] power-of-two weight scales, then [kNumSc] their inverses
+  unsigned char* wimg;      // [kNumImg] fp16 block images
+  float* p0f;               // [2B][P][64]  30 * W0f[:, :64] * flow_feat
+  float* p0i;               // [2B][P][64]  30 * W0i[:, :64] * feat
+  float* ftab;              // [2B][P][64]  30 * W0b * feat
+  float* rtab;              // [B][P][64]   30 * (W0c * residual + b0)
+  float* Y;                 // [2B][qs][64] 30 * (W0a*imnet(q) + W0b*feat[nearest(q)]) per source pixel
+  float* side;              // [B][qs][4]   sum e*dx*w, sum e*dy*w, sum e*w, count
+  float* zmax;              // [B][qs]      max splat of e, starts at 1
+  int* bin_count;           // [B][qs]
+  uint2* bin_ent;           // [B][qs][kSlots] (source id, e*w)
+  float* spill;             // [B][qs][64]  contributions that found no list slot
+};
+
+static int layout(int B, int H, int W, int HH, int WW, Scratch* s, char* base, size_t* bytes) {
+  const size_t qs = (size_t)HH * WW, P = (size_t)H * W;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    char* p = base ? base + off : nullptr;
+    off += (nbytes + 1023) & ~size_t(1023);
+    return p;
+  };
+  Scratch t;
+  t.wpack = (float*)take(sizeof(float) * WeightPack::total);
+  t.fold = (float*)take(sizeof(float) * (64 * 256 + 64));
+  t.scales = (float*)take(sizeof(float) * 2 * kNumSc);
+  t.wimg = (unsigned char*)take((size_t)kNumImg * kBlkBytes);
+  t.p0f = (float*)take(sizeof(float) * 2 * B * P * 64);
+  t.p0i = (float*)take(sizeof(float) * 2 * B * P * 64);
+  t.ftab = (float*)take(sizeof(float) * 2 * B * P * 64);
+  t.rtab = (float*)take(sizeof(float) * B * P * 64);
+  t.Y = (float*)take(sizeof(float) * 2 * B * qs * 64);
+  t.side = (float*)take(sizeof(float) * B * qs * 4);
+  t.zmax = (float*)take(sizeof(float) * B * qs);
+  t.bin_count = (int*)take(sizeof(int) * B * qs);
+  t.bin_ent = (uint2*)take(sizeof(uint2) * B * qs * kSlots);
+  t.spill = (float*)take(sizeof(float) * B * qs * 64);
+  if (s) *s = t;
+  if (bytes) *bytes = off;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// One-time preparation kernels (per decode call; all tiny)
+// ------------------------------------------------------------------------------------------------------
+// fold[o][k] = sum_m W0a[o][m] * W3[m][k]  (synth_net layer 0, columns 0..63, composed with imnet's output layer)
+__global__ void fold_kernel(const float* __restrict__ wp, float* __restrict__ fold) {
+  const int o = blockIdx.x, k = threadIdx.x;
+  const float* w0a = wp + WeightPack::s_a0a + o * 64;
+  double acc = 0.0;
+  for (int m = 0; m < 64; ++m) acc += (double)w0a[m] * (double)wp[WeightPack::i_a3 + m * 256 + k];
+  fold[o * 256 + k] = (float)acc;
+  if (k == 0) {
+    double b = 0.0;
+    for (int m = 0; m < 64; ++m) b += (double)w0a[m] * (double)wp[WeightPack::i_b3 + m];
+    fold[64 * 256 + o] = (float)b;
+  }
+}
+
+struct MatRef {
+  int in_fold;  // 0: wpack, 1: fold
+  int off, count;
+};
+struct ScaleJobs {
+  MatRef m[kNumSc];
+};
+// scale = 2^(13 - floor(log2 max|w|)): the largest weight lands in [2^13, 2^14), inside fp16's normal range with
+// 13 binades of headroom below for the lo pieces.
+__global__ void scale_kernel(ScaleJobs jobs, const float* __restrict__ wp, const float* __restrict__ fold, float* __restrict__ scales) {
+  __shared__ float red[256];
+  const MatRef mr = jobs.m[blockIdx.x];
+  const float* src = (mr.in_fold ? fold : wp) + mr.off;
+  float mx = 0.0f;
+  for (int i = threadIdx.x; i < mr.count; i += blockDim.x) {
+    const float a = fabsf(src[i]);
+    if (a < 3.0e38f) mx = fmaxf(mx, a);
+  }
+  red[threadIdx.x] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float m = red[0];
+    float sc = 1.0f;
+    if (m > 0.0f) sc = exp2f((float)(13 - ilogbf(m)));
+    if (!(sc > 1.0e-30f && sc < 1.0e30f)) sc = 1.0f;
+    scales[blockIdx.x] = sc;
+    scales[kNumSc + blockIdx.x] = 1.0f / sc;
+  }
+}
+
+struct ImgJob {
+  int in_fold, off, ldw, n0, k0, sc;
+};
+struct ImgJobs {
+  ImgJob j[kNumImg];
+};
+__global__ void pack_images_kernel(ImgJobs jobs, const float* __restrict__ wp, const float* __restrict__ fold, const float* __restrict__ scales,
+                                   unsigned char* __restrict__ wimg) {
+  const ImgJob jb = jobs.j[blockIdx.x];
+  const float* src = (jb.in_fold ? fold : wp) + jb.off;
+  const float sc = scales[jb.sc];
+  unsigned char* dst = wimg + (size_t)blockIdx.x * kBlkBytes;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int n = i >> 6, k = i & 63;
+    const float v = src[(size_t)(jb.n0 + n) * jb.ldw + jb.k0 + k] * sc;  // exact (power of two)
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const uint32_t off = sw128_offset_h(n, k);
+    *reinterpret_cast<__half*>(dst + off) = hi;
+    *reinterpret_cast<__half*>(dst + kBlkHalf + off) = lo;
+  }
+}
+
+// out[p][o] = 30 * (sum_k w[o][k] * x[p][k] + bias[o]) for one [64][64] weight block and one pixel-major LR tensor.
+struct LrJob {
+  const float* x;
+  float* out;
+  int w_off, bias_off, bias_ld;  // bias_off < 0: none
+};
+struct LrJobs {
+  LrJob j[16];
+};
+__global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float* __restrict__ wp, int P) {
+  __shared__ float4 w4[64 * 16];
+  __shared__ float bias[64];
+  const LrJob jb = jobs.j[blockIdx.y];
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) w4[i] = *reinterpret_cast<const float4*>(wp + jb.w_off + 4 * i);
+  if (threadIdx.x < 64) bias[threadIdx.x] = jb.bias_off >= 0 ? wp[jb.bias_off + threadIdx.x * jb.bias_ld] : 0.0f;
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float x[64];
+  const float4* xr = reinterpret_cast<const float4*>(jb.x + (size_t)p * 64);
+#pragma unroll
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const float4 v = __ldg(xr + k4);
+    x[4 * k4] = v.x, x[4 * k4 + 1] = v.y, x[4 * k4 + 2] = v.z, x[4 * k4 + 3] = v.w;
+  }
+  float4* o4 = reinterpret_cast<float4*>(jb.out + (size_t)p * 64);
+#pragma unroll 1
+  for (int o0 = 0; o0 < 64; o0 += 4) {
+    float r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < 16; ++k4) {
+        const float4 w = w4[(o0 + u) * 16 + k4];
+        a0 = fmaf(w.x, x[4 * k4], a0);
+        a1 = fmaf(w.y, x[4 * k4 + 1], a1);
+        a0 = fmaf(w.z, x[4 * k4 + 2], a0);
+        a1 = fmaf(w.w, x[4 * k4 + 3], a1);
+      }
+      r[u] = ((a0 + a1) + bias[o0 + u]) * kOmega;
+    }
+    o4[o0 >> 2] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+__global__ void fill_kernel(float* p, float v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Shared-memory carve-up, barriers, MMA issue program
+// ------------------------------------------------------------------------------------------------------
+struct Bars {
+  uint64_t w_full;
+  uint64_t a_ready[2], a2_ready[2], a2_free[2];
+  uint64_t d_ready[2][2], d_free[2][2];
+  uint32_t tmem_base;
+};
+
+struct Step {
+  unsigned char img;       // weight block (index into the kernel's resident images)
+  unsigned char dbuf;      // accumulator D0 / D1
+  unsigned char a_src;     // 0: A columns, 1: A2 columns, 2: shared-memory tile
+  unsigned char wait_a;    // 0: none, 1: a_ready, 2: a2_ready
+  unsigned char acc;       // accumulate into D (else overwrite after waiting d_free)
+  unsigned char commit_d;  // commit d_ready[dbuf] after this block
+  unsigned char commit_a2; // commit a2_free after this block
+};
+
+template <int NIMG, int EXTRA_BYTES>
+struct Smem {
+  unsigned char img[NIMG][kBlkBytes];  // must stay first (1024-byte aligned swizzle atoms)
+  unsigned char extra[EXTRA_BYTES > 0 ? EXTRA_BYTES : 16];
+  float consts[2048];
+  Bars bars;
+};
+
+__device__ __forceinline__ unsigned char* align1024(unsigned char* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+
+__device__ __forceinline__ void init_bars(Bars& b) {
+  mbar_init(&b.w_full, 1);
+  for (int t = 0; t < 2; ++t) {
+    mbar_init(&b.a_ready[t], 128);
+    mbar_init(&b.a2_ready[t], 128);
+    mbar_init(&b.a2_free[t], 1);
+    for (int d = 0; d < 2; ++d) {
+      mbar_init(&b.d_ready[t][d], 1);
+      mbar_init(&b.d_free[t][d], 128);
+    }
+  }
+  fence_mbar_init();
+}
+
+__device__ __forceinline__ uint32_t setup(Bars& bars) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) init_bars(bars);
+  if (warp == 2) tmem_alloc<512>(&bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return bars.tmem_base;
+}
+__device__ __forceinline__ void teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// warp 0, one lane: bring the kernel's weight images in with one bulk copy each
+__device__ __forceinline__ void load_images(unsigned char* dst, const unsigned char* wimg, int img0, int n_img, Bars& bars) {
+  mbar_arrive_expect_tx(&bars.w_full, (uint32_t)n_img * kBlkBytes);
+  for (int i = 0; i < n_img; ++i) bulk_g2s(dst + (size_t)i * kBlkBytes, wimg + (size_t)(img0 + i) * kBlkBytes, kBlkBytes, &bars.w_full);
+}
+
+// warp 1, one lane.  a_tile_smem: base of the two shared-memory A tiles (hi 16 KB + lo 16 KB each) for a_src == 2.
+template <int NSTEPS>
+__device__ __forceinline__ void issuer_loop(Bars& bars, const unsigned char* img_base, const unsigned char* a_tile_smem, const Step (&prog)[NSTEPS],
+                                            int n_iters, uint32_t tmem_base) {
+  const uint32_t idesc = idesc_f16(128, 64);
+  uint32_t ph_a[2] = {0, 0}, ph_a2[2] = {0, 0};
+  uint32_t ph_dfree[2][2] = {{1, 1}, {1, 1}};  // buffers start free
+  mbar_wait(&bars.w_full, 0);
+  for (int it = 0; it < n_iters; ++it) {
+#pragma unroll 1
+    for (int s = 0; s < NSTEPS; ++s) {
+      const Step st = prog[s];
+      const uint32_t bhi = smem_u32(img_base + (size_t)st.img * kBlkBytes);
+      const uint32_t blo = bhi + kBlkHalf;
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile) {
+        const uint32_t tbase = tmem_base + tile * kTileCols;
+        if (st.wait_a == 1) {
+          mbar_wait(&bars.a_ready[tile], ph_a[tile]);
+          ph_a[tile] ^= 1;
+        } else if (st.wait_a == 2) {
+          mbar_wait(&bars.a2_ready[tile], ph_a2[tile]);
+          ph_a2[tile] ^= 1;
+        }
+        if (!st.acc) {
+          mbar_wait(&bars.d_free[tile][st.dbuf], ph_dfree[tile][st.dbuf]);
+          ph_dfree[tile][st.dbuf] ^= 1;
+        }
+        tc_fence_after();
+        const uint32_t dcol = tbase + kColD0 + 64 * st.dbuf;
+        bool acc = st.acc != 0;
+        if (st.a_src == 2) {
+          const uint32_t ahi = smem_u32(a_tile_smem + (size_t)tile * kBlkBytes * 2);  // tile: 128 rows x 128 B hi, then lo
+          const uint32_t alo = ahi + 2 * kBlkHalf;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a = (term == 1) ? alo : ahi;
+            const uint32_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_f16_ss(dcol, smem_desc_sw128(a + ks * 32), smem_desc_sw128(b + ks * 32), idesc, acc);
+              acc = true;
+            }
+          }
+        } else {
+          const uint32_t ahi = tbase + (st.a_src == 1 ? kColA2 : kColA);
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a = (term == 1) ? ahi + 32 : ahi;
+            const uint32_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_f16_ts(dcol, a + ks * 8, smem_desc_sw128(b + ks * 32), idesc, acc);
+              acc = true;
+            }
+          }
+        }
+        if (st.commit_d) mma_commit(&bars.d_ready[tile][st.dbuf]);
+        if (st.commit_a2) mma_commit(&bars.a2_free[tile]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Epilogue helpers (128 threads per tile; thread <-> TMEM lane)
+// ------------------------------------------------------------------------------------------------------
+struct Epi {
+  Bars* bars;
+  int tile;
+  uint32_t lane_addr;  // TMEM address of this thread's lane, column 0 of its tile
+  uint32_t ph_dready[2];
+  uint32_t ph_a2free;
+};
+
+__device__ __forceinline__ Epi make_epi(Bars& bars, uint32_t tmem_base) {
+  const int warp = threadIdx.x >> 5;
+  Epi c;
+  c.bars = &bars;
+  c.tile = (warp - kEpiWarp0) >> 2;
+  c.lane_addr = tmem_base + c.tile * kTileCols + ((uint32_t)((warp & 3) * 32) << 16);
+  c.ph_dready[0] = c.ph_dready[1] = 0;
+  c.ph_a2free = 1;  // A2 starts free
+  return c;
+}
+__device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
+
+__device__ __forceinline__ void wait_d(Epi& c, int dbuf) {
+  mbar_wait(&c.bars->d_ready[c.tile][dbuf], c.ph_dready[dbuf]);
+  c.ph_dready[dbuf] ^= 1;
+  tc_fence_after();
+}
+__device__ __forceinline__ void release_d(Epi& c, int dbuf) {
+  tc_fence_before();
+  mbar_arrive(&c.bars->d_free[c.tile][dbuf]);
+}
+__device__ __forceinline__ void publish(Epi& c, uint64_t* bar) {
+  tmem_wait_st();
+  tc_fence_before();
+  mbar_arrive(bar);
+}
+
+// fp32 pair -> fp16 hi pair + fp16 lo pair (lo = fp16 of the exact fp32 remainder)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(__fsub_rn(a, f.x), __fsub_rn(b, f.y));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 16 consecutive K values of this thread's row -> 8 hi and 8 lo columns at `acol` (hi) and `acol + 32` (lo)
+__device__ __forceinline__ void split_store16(uint32_t acol, const float (&v)[16]) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+  tmem_st8(acol, hi);
+  tmem_st8(acol + 32, lo);
+}
+
+// First layer from the LR table: v = sin(P0'[row] + e.x + e.y * rel_y + e.z * rel_x) (everything pre-scaled by 30)
+__device__ __forceinline__ void table_layer0(Epi& c, const float* __restrict__ p0row, const float4* __restrict__ e0, float rel_y, float rel_x) {
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(p0row + c0) + j4);
+      const float pv[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 e = e0[c0 + 4 * j4 + u];
+        v[4 * j4 + u] = __sinf(pv[u] + fmaf(e.z, rel_x, fmaf(e.y, rel_y, e.x)));
+      }
+    }
+    split_store16(c.lane_addr + kColA + c0 / 2, v);
+  }
+  publish(c, &c.bars->a_ready[c.tile]);
+}
+
+// 64 -> 64 sine layer: D[dbuf] -> sin(s * D + cb) -> A.   s = 30 / weight scale, cb = 30 * bias (smem)
+__device__ __forceinline__ void sine_epilogue(Epi& c, int dbuf, float s, const float* __restrict__ cb) {
+  wait_d(c, dbuf);
+  uint32_t r[64];
+  tmem_ld64(c.lane_addr + kColD0 + 64 * dbuf, r);
+  release_d(c, dbuf);
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = *reinterpret_cast<const float4*>(cb + c0 + 4 * j4);
+      v[4 * j4 + 0] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 0]), s, b.x));
+      v[4 * j4 + 1] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 1]), s, b.y));
+      v[4 * j4 + 2] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 2]), s, b.z));
+      v[4 * j4 + 3] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 3]), s, b.w));
+    }
+    split_store16(c.lane_addr + kColA + c0 / 2, v);
+  }
+  publish(c, &c.bars->a_ready[c.tile]);
+}
+
+// 64 hidden units of a 64 -> 256 sine layer followed by the 256 -> 3 linear layer on CUDA cores.
+// cw[j] = (30 * bias_j, w_out[0][j], w_out[1][j], w_out[2][j]) (smem)
+__device__ __forceinline__ void sine_out3_epilogue(Epi& c, int dbuf, float s, const float4* __restrict__ cw, float& o0, float& o1, float& o2) {
+  wait_d(c, dbuf);
+  uint32_t r[64];
+  tmem_ld64(c.lane_addr + kColD0 + 64 * dbuf, r);
+  release_d(c, dbuf);
+  float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const float4 w = cw[j];
+    const float v = __sinf(fmaf(__uint_as_float(r[j]), s, w.x));
+    p0[j & 3] = fmaf(v, w.y, p0[j & 3]);
+    p1[j & 3] = fmaf(v, w.z, p1[j & 3]);
+    p2[j & 3] = fmaf(v, w.w, p2[j & 3]);
+  }
+  o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
+  o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+  o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+}
+
+// ======================================================================================================
+// imnet (once per clip).  Tile 0 / 1 = reference frame 0 / 1 of the same 128 pixels.
+//   Y[rb][q] = 30 * (W0a * imnet(q) + W0b * feat[nearest(q)])   (synth_net layer-0 contribution of source pixel q)
+// ======================================================================================================
+constexpr int kNumStepsI = 9;
+__constant__ Step kProgI[kNumStepsI] = {
+    // img dbuf a_src wait_a acc commit_d commit_a2
+    {0, 0, 0, 1, 0, 1, 0},  // layer 1                                  -> D0
+    {1, 0, 0, 1, 0, 1, 0},  // layer 2 units 0..63                      -> D0
+    {2, 0, 0, 0, 0, 1, 0},  // layer 2 units 64..127                    -> D0 (after the epilogue drained chunk 0)
+    {5, 1, 1, 2, 0, 0, 1},  // output layer K block 0 (A2 = sin chunk 0) -> D1
+    {3, 0, 0, 0, 0, 1, 0},  // layer 2 units 128..191
+    {6, 1, 1, 2, 1, 0, 1},
+    {4, 0, 0, 0, 0, 1, 0},  // layer 2 units 192..255
+    {7, 1, 1, 2, 1, 0, 1},
+    {8, 1, 1, 2, 1, 1, 1},  // last K block completes D1
+};
+using SmemI = Smem<9, 0>;
+
+// consts: [0,256) e0 float4 (30 b0, 30 w_rely, 30 w_relx, 0)  [256,320) 30 b1  [320,576) 30 b2  [576,640) 30 * folded bias
+//         [640] s1  [641] s2  [642] s3
+__global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, int B, int b, Scratch sc) {
+  extern __shared__ unsigned char smem_raw[];
+  SmemI& sm = *reinterpret_cast<SmemI*>(align1024(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW, P = g.H * g.W;
+  const int n_tiles = (qs + 127) / 128;
+  const int n_iters = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const float* wp = sc.wpack;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::i_e0 + 4 * i);
+    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(e.x * kOmega, e.y * kOmega, e.z * kOmega, 0.f);
+    sm.consts[256 + i] = wp[WeightPack::i_b1 + i] * kOmega;
+    sm.consts[576 + i] = sc.fold[64 * 256 + i] * kOmega;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.consts[320 + i] = wp[WeightPack::i_b2 + i] * kOmega;
+  if (threadIdx.x < 3) sm.consts[640 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScI1 + threadIdx.x];
+  const uint32_t tmem_base = setup(sm.bars);
+
+  if (warp == 0) {
+    if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgI1, 9, sm.bars);
+  } else if (warp == 1) {
+    if (lane == 0) issuer_loop(sm.bars, &sm.img[0][0], nullptr, kProgI, n_iters, tmem_base);
+  } else if (warp >= kEpiWarp0) {
+    Epi c = make_epi(sm.bars, tmem_base);
+    const int rb = c.tile * B + b;
+    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
+    const float s1 = sm.consts[640], s2 = sm.consts[641], s3 = sm.consts[642];
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile_id = blockIdx.x + it * gridDim.x;
+      const int q = tile_id * 128 + epi_row();
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      const Query qu = make_query(qc / g.WW, qc % g.WW, g);
+      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
+      table_layer0(c, sc.p0i + lr * 64, e0, qu.rel_y, qu.rel_x);
+      sine_epilogue(c, 0, s1, sm.consts + 256);
+      // layer 2 chunk -> sine -> A2 (the K block of the output layer)
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        wait_d(c, 0);
+        uint32_t r[64];
+        tmem_ld64(c.lane_addr + kColD0, r);
+        release_d(c, 0);
+        mbar_wait(&sm.bars.a2_free[c.tile], c.ph_a2free);
+        c.ph_a2free ^= 1;
+        tc_fence_after();
+        const float* cb = sm.consts + 320 + 64 * ch;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __sinf(fmaf(__uint_as_float(r[c0 + j]), s2, cb[c0 + j]));
+          split_store16(c.lane_addr + kColA2 + c0 / 2, v);
+        }
+        publish(c, &sm.bars.a2_ready[c.tile]);
+      }
+      // output: Y = s3 * D1 + 30 * bias' + 30 * W0b * feat[nearest]
+      wait_d(c, 1);
+      {
+        uint32_t r[64];
+        tmem_ld64(c.lane_addr + kColD0 + 64, r);
+        release_d(c, 1);
+        const float4* f4 = reinterpret_cast<const float4*>(sc.ftab + lr * 64);
+        float4* dst = reinterpret_cast<float4*>(sc.Y + ((size_t)rb * qs + qc) * 64);
+        if (live) {
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 f = __ldg(f4 + j4);
+            const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 576 + 4 * j4);
+            dst[j4] = make_float4(fmaf(__uint_as_float(r[4 * j4 + 0]), s3, bb.x) + f.x, fmaf(__uint_as_float(r[4 * j4 + 1]), s3, bb.y) + f.y,
+                                  fmaf(__uint_as_float(r[4 * j4 + 2]), s3, bb.z) + f.z, fmaf(__uint_as_float(r[4 * j4 + 3]), s3, bb.w) + f.w);
+          }
+        }
+      }
+    }
+  }
+  teardown(tmem_base);
+}
+
+// ======================================================================================================
+// flow_imnet + binning of the three forward splats (per timestamp).  Tile 0 / 1 = reference frame 0 / 1.
+// ======================================================================================================
+constexpr int kNumStepsF = 5;
+__constant__ Step kProgF[kNumStepsF] = {
+    {0, 0, 0, 1, 0, 1, 0},  // layer 1
+    {1, 0, 0, 1, 0, 1, 0},  // layer 2 units 0..63    -> D0
+    {2, 1, 0, 0, 0, 1, 0},  //         units 64..127  -> D1
+    {3, 0, 0, 0, 0, 1, 0},  //         units 128..191 -> D0
+    {4, 1, 0, 0, 0, 1, 0},  //         units 192..255 -> D1
+};
+using SmemF = Smem<5, 0>;
+
+// consts: [0,256) e0 float4 (30 (b0 + w_t t), 30 w_rely, 30 w_relx, 0)  [256,320) 30 b1
+//         [320,1344) float4 per hidden unit (30 b2, w3[0], w3[1], w3[2])  [1344,1347) b3  [1348] s1 [1349] s2
+__global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t g, int B, int N, int n, int b, float t, float alpha, Scratch sc,
+                                                                  float* __restrict__ flow_out) {
+  extern __shared__ unsigned char smem_raw[];
+  SmemF& sm = *reinterpret_cast<SmemF*>(align1024(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW, P = g.H * g.W;
+  const int n_tiles = (qs + 127) / 128;
+  const int n_iters = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const float* wp = sc.wpack;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * i);
+    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(fmaf(e.y, t, e.x) * kOmega, e.z * kOmega, e.w * kOmega, 0.f);
+    sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<float4*>(sm.consts + 320)[i] =
+        make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 512 + i]);
+  if (threadIdx.x < 3) sm.consts[1344 + threadIdx.x] = wp[WeightPack::f_b3 + threadIdx.x];
+  if (threadIdx.x < 2) sm.consts[1348 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScF1 + threadIdx.x];
+  const uint32_t tmem_base = setup(sm.bars);
+
+  if (warp == 0) {
+    if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgF1, 5, sm.bars);
+  } else if (warp == 1) {
+    if (lane == 0) issuer_loop(sm.bars, &sm.img[0][0], nullptr, kProgF, n_iters, tmem_base);
+  } else if (warp >= kEpiWarp0) {
+    Epi c = make_epi(sm.bars, tmem_base);
+    const int r = c.tile;
+    const int rb = r * B + b;
+    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
+    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
+    const float s1 = sm.consts[1348], s2 = sm.consts[1349];
+    for (int it = 0; it < n_iters; ++it) {
+      const int tile_id = blockIdx.x + it * gridDim.x;
+      const int q = tile_id * 128 + epi_row();
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      const int qy = qc / g.WW, qx = qc % g.WW;
+      const Query qu = make_query(qy, qx, g);
+      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
+      table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
+      sine_epilogue(c, 0, s1, sm.consts + 256);
+      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s2, cw + 64 * ch, dx, dy, zraw);
+
+      // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
+      const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
+      const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
+      const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
+      const float e = expf(z);
+      if (live && flow_out != nullptr) {
+        float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
+        fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
+        fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
+      }
+      const Footprint f = footprint(qx, qy, fx, fy);
+      if (live && f.finite) {
+        const uint32_t id = (uint32_t)((size_t)rb * qs + q);
+        const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
+          if ((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH)) continue;
+          const size_t d = (size_t)b * qs + (size_t)cy * g.WW + cx;
+          const float wk = f.w[k];
+          const float we = __fmul_rn(e, wk);
+          const int slot = atomicAdd(sc.bin_count + d, 1);
+          if (slot < kSlots) {
+            sc.bin_ent[d * kSlots + slot] = make_uint2(id, __float_as_uint(we));
+          } else {
+            const float4* y4 = reinterpret_cast<const float4*>(sc.Y + (size_t)id * 64);
+            float* sp = sc.spill + d * 64;
+#pragma unroll 4
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 y = __ldg(y4 + j4);
+              red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
+            }
+          }
+          red_add_v4(sc.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
+          // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
+          if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
+        }
+      }
+    }
+  }
+  teardown(tmem_base);
+}
+
+// ======================================================================================================
+// gather + blend + synth_net (per timestamp).  Tiles 0 / 1 are two consecutive 128-pixel destination tiles.
+// ======================================================================================================
+constexpr int kNumStepsS = 6;
+__constant__ Step kProgS[kNumStepsS] = {
+    {0, 0, 2, 1, 0, 1, 0},  // layer 1, A = sin(layer-0 pre-activation) from the shared-memory tile
+    {1, 0, 0, 1, 0, 1, 0},  // layer 2
+    {2, 0, 0, 1, 0, 1, 0},  // layer 3 units 0..63    -> D0
+    {3, 1, 0, 0, 0, 1, 0},  //         units 64..127  -> D1
+    {4, 0, 0, 0, 0, 1, 0},
+    {5, 1, 0, 0, 0, 1, 0},
+};
+struct WarpStage {
+  uint2 ent[32][kSlots];  // list entries of the warp's 32 destinations
+  float4 par[32][2];      // (1/wz, dx', dy', zmax), (count/16, wz/count, lr index bits, count bits)
+};
+constexpr int kSynthExtra = 2 * 2 * kBlkBytes + 8 * (int)sizeof(WarpStage);  // two A tiles (hi+lo, 128 rows) + staging
+using SmemS = Smem<6, kSynthExtra>;
+
+// consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) float4 per hidden unit (30 b3, w4[0], w4[1], w4[2])  [1152,1155) b4
+//         [1156] s1  [1157] s2  [1158] s3
+__global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, int B, int N, int n, int b, float t, Scratch sc, float* __restrict__ rgb,
+                                                               float* __restrict__ dbg_pre0) {
+  extern __shared__ unsigned char smem_raw[];
+  SmemS& sm = *reinterpret_cast<SmemS*>(align1024(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW, P = g.H * g.W;
+  const int n_units = (qs + 255) / 256;
+  const int n_iters = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const float* wp = sc.wpack;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    sm.consts[i] = wp[WeightPack::s_b1 + i] * kOmega;
+    sm.consts[64 + i] = wp[WeightPack::s_b2 + i] * kOmega;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<float4*>(sm.consts + 128)[i] =
+        make_float4(wp[WeightPack::s_b3 + i] * kOmega, wp[WeightPack::s_a4 + i], wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 512 + i]);
+  if (threadIdx.x < 3) {
+    sm.consts[1152 + threadIdx.x] = wp[WeightPack::s_b4 + threadIdx.x];
+    sm.consts[1156 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScS1 + threadIdx.x];
+  }
+  const uint32_t tmem_base = setup(sm.bars);
+  unsigned char* a_tiles = sm.extra;  // 1024-aligned: follows the images
+
+  if (warp == 0) {
+    if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgS1, 6, sm.bars);
+  } else if (warp == 1) {
+    if (lane == 0) issuer_loop(sm.bars, &sm.img[0][0], a_tiles, kProgS, n_iters, tmem_base);
+  } else if (warp >= kEpiWarp0) {
+    Epi c = make_epi(sm.bars, tmem_base);
+    WarpStage& ws = reinterpret_cast<WarpStage*>(sm.extra + 2 * 2 * kBlkBytes)[warp - kEpiWarp0];
+    unsigned char* a_hi = a_tiles + (size_t)c.tile * 2 * kBlkBytes;
+    unsigned char* a_lo = a_hi + 2 * kBlkHalf;
+    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
+    const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
+    const int bn = b * N + n;
+    // rank-1 input weights of this lane's two channels (2 lane, 2 lane + 1), pre-scaled by 30:
+    // s_e0[ch] = (bias [in rtab], w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t, 0)
+    float rk[2][5], ct[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float* e = wp + WeightPack::s_e0 + 8 * (2 * lane + u);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) rk[u][i] = e[1 + i] * kOmega;
+      ct[u] = e[6] * t * kOmega;
+    }
+    const float2* Y2 = reinterpret_cast<const float2*>(sc.Y);
+    const float2* R2 = reinterpret_cast<const float2*>(sc.rtab);
+    for (int it = 0; it < n_iters; ++it) {
+      const int unit = blockIdx.x + it * gridDim.x;
+      const int q_w = unit * 256 + c.tile * 128 + (warp & 3) * 32;  // first destination of this warp
+      const int q = q_w + lane;
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      // ---- per-destination scalars (Ours.py:813-814, 826-829, 834), re-arm the accumulators ----
+      {
+        const size_t d = (size_t)b * qs + qc;
+        float4 side = make_float4(0.f, 0.f, 0.f, 0.f);
+        float zm = 1.0f;
+        int cnt_i = 0;
+        if (live) {
+          float4* side_p = reinterpret_cast<float4*>(sc.side + d * 4);
+          side = *side_p;
+          zm = sc.zmax[d];
+          cnt_i = sc.bin_count[d];
+          *side_p = make_float4(0.f, 0.f, 0.f, 0.f);
+          sc.zmax[d] = 1.0f;
+          sc.bin_count[d] = 0;
+        }
+        const float wz = side.z == 0.0f ? 1.0f : side.z;
+        const float cnt = (float)cnt_i;
+        const float cnt_ = cnt == 0.0f ? 1.0f : cnt;
+        const float wz_ = wz == 1.0f ? 0.0f : wz;
+        const float inv_wz = __fdiv_rn(1.0f, wz);
+        const Query qu = make_query(qc / g.WW, qc % g.WW, g);
+        const int lr = qu.iy * g.W + qu.ix;
+        ws.par[lane][0] = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
+        ws.par[lane][1] = make_float4(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_), __int_as_float(lr), __int_as_float(live ? cnt_i : -1));
+        // the 32 lists of this warp are contiguous: copy them with coalesced 16-byte loads
+        const uint4* src = reinterpret_cast<const uint4*>(sc.bin_ent + ((size_t)b * qs + q_w) * kSlots);
+        uint4* dst = reinterpret_cast<uint4*>(&ws.ent[0][0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = i * 32 + lane;
+          dst[idx] = (q_w + (idx >> 3) < qs) ? __ldg(src + idx) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      __syncwarp();
+      // ---- cooperative gather: one destination at a time, lane = channel pair ----
+#pragma unroll 1
+      for (int j = 0; j < 32; ++j) {
+        const float4 pa = ws.par[j][0], pb = ws.par[j][1];
+        const int cnt_i = __float_as_int(pb.w);
+        const int cnt = min(cnt_i, kSlots);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int k0 = 0; k0 < cnt; k0 += 8) {
+          float2 y[8];
+          float we[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint2 en = ws.ent[j][(k0 + k) & (kSlots - 1)];
+            const bool on = k0 + k < cnt;
+            we[k] = on ? __uint_as_float(en.y) : 0.0f;
+            y[k] = on ? __ldg(Y2 + (size_t)en.x * 32 + lane) : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            acc.x = fmaf(we[k], y[k].x, acc.x);
+            acc.y = fmaf(we[k], y[k].y, acc.y);
+          }
+        }
+        const int dq = q_w + j;
+        if (cnt_i > kSlots) {  // spilled contributions of an overfull list
+          float2* sp = reinterpret_cast<float2*>(sc.spill + ((size_t)b * qs + dq) * 64) + lane;
+          const float2 v = *sp;
+          acc.x += v.x;
+          acc.y += v.y;
+          *sp = make_float2(0.f, 0.f);
+        }
+        const float2 rr = __ldg(R2 + ((size_t)b * P + __float_as_int(pb.z)) * 32 + lane);
+        float pre[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float lin = fmaf(rk[u][0], pa.y, fmaf(rk[u][1], pa.z, fmaf(rk[u][2], pa.w, fmaf(rk[u][3], pb.x, fmaf(rk[u][4], pb.y, ct[u])))));
+          pre[u] = fmaf(u == 0 ? acc.x : acc.y, pa.x, (u == 0 ? rr.x : rr.y) + lin);
+        }
+        if (dbg_pre0 != nullptr && cnt_i >= 0) {
+          dbg_pre0[((size_t)bn * 64 + 2 * lane) * qs + dq] = pre[0] * (1.0f / kOmega);
+          dbg_pre0[((size_t)bn * 64 + 2 * lane + 1) * qs + dq] = pre[1] * (1.0f / kOmega);
+        }
+        uint32_t hi, lo;
+        split_pair(__sinf(pre[0]), __sinf(pre[1]), hi, lo);
+        const int row = (warp & 3) * 32 + j;
+        const uint32_t off = sw128_offset_h(row, 2 * lane);
+        *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+        *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.bars.a_ready[c.tile]);
+      // ---- layers 1..3 and the output layer, thread per pixel ----
+      sine_epilogue(c, 0, s1, sm.consts);
+      sine_epilogue(c, 0, s2, sm.consts + 64);
+      float o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s3, cw + 64 * ch, o0, o1, o2);
+      if (live) {
+        float* out = rgb + ((size_t)(n * B + b) * 3) * qs + q;
+        out[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
+        out[(size_t)qs] = fminf(fmaxf(o1, 0.0f), 1.0f);
+        out[(size_t)2 * qs] = fminf(fmaxf(o2, 0.0f), 1.0f);
+      }
+    }
+  }
+  teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) {
+  using Wp = WeightPack;
+  const motif_geom_t& g = a->geom;
+  const int P = g.H * g.W, B = g.B;
+  if (int rc = pack_weights(a, sc.wpack, st)) return rc;
+  fold_kernel<<<64, 256, 0, st>>>(sc.wpack, sc.fold);
+  MOTIF_LAUNCHED("fold_kernel");
+  ScaleJobs sj;
+  sj.m[kScF1] = MatRef{0, Wp::f_a1, 64 * 64};
+  sj.m[kScF2] = MatRef{0, Wp::f_a2, 256 * 64};
+  sj.m[kScI1] = MatRef{0, Wp::i_a1, 64 * 64};
+  sj.m[kScI2] = MatRef{0, Wp::i_a2, 256 * 64};
+  sj.m[kScI3] = MatRef{1, 0, 64 * 256};
+  sj.m[kScS1] = MatRef{0, Wp::s_a1, 64 * 64};
+  sj.m[kScS2] = MatRef{0, Wp::s_a2, 64 * 64};
+  sj.m[kScS3] = MatRef{0, Wp::s_a3, 256 * 64};
+  scale_kernel<<<kNumSc, 256, 0, st>>>(sj, sc.wpack, sc.fold, sc.scales);
+  MOTIF_LAUNCHED("scale_kernel");
+  ImgJobs ij;
+  int k = 0;
+  auto add = [&](int in_fold, int off, int ldw, int n0, int k0, int scale) { ij.j[k++] = ImgJob{in_fold, off, ldw, n0, k0, scale}; };
+  add(0, Wp::f_a1, 64, 0, 0, kScF1);
+  for (int c = 0; c < 4; ++c) add(0, Wp::f_a2, 64, 64 * c, 0, kScF2);
+  add(0, Wp::i_a1, 64, 0, 0, kScI1);
+  for (int c = 0; c < 4; ++c) add(0, Wp::i_a2, 64, 64 * c, 0, kScI2);
+  for (int c = 0; c < 4; ++c) add(1, 0, 256, 0, 64 * c, kScI3);
+  add(0, Wp::s_a1, 64, 0, 0, kScS1);
+  add(0, Wp::s_a2, 64, 0, 0, kScS2);
+  for (int c = 0; c < 4; ++c) add(0, Wp::s_a3, 64, 64 * c, 0, kScS3);
+  pack_images_kernel<<<kNumImg, 256, 0, st>>>(ij, sc.wpack, sc.fold, sc.scales, sc.wimg);
+  MOTIF_LAUNCHED("pack_images_kernel");
+  // LR tables
+  LrJobs lj;
+  int nj = 0;
+  for (int rb = 0; rb < 2 * B; ++rb) {
+    lj.j[nj++] = LrJob{a->flow_feat + (size_t)rb * P * 64, sc.p0f + (size_t)rb * P * 64, Wp::f_a0, -1, 0};
+    lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.p0i + (size_t)rb * P * 64, Wp::i_a0, -1, 0};
+    lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.ftab + (size_t)rb * P * 64, Wp::s_a0b, -1, 0};
+    if (nj + 4 > 16) {
+      lr_tables_kernel<<<dim3(ceil_div(P, 128), nj), 128, 0, st>>>(lj, sc.wpack, P);
+      MOTIF_LAUNCHED("lr_tables_kernel");
+      nj = 0;
+    }
+  }
+  for (int b = 0; b < B; ++b) {
+    lj.j[nj++] = LrJob{a->residual + (size_t)b * P * 64, sc.rtab + (size_t)b * P * 64, Wp::s_a0c, Wp::s_e0, 8};
+    if (nj == 16) {
+      lr_tables_kernel<<<dim3(ceil_div(P, 128), nj), 128, 0, st>>>(lj, sc.wpack, P);
+      MOTIF_LAUNCHED("lr_tables_kernel");
+      nj = 0;
+    }
+  }
+  if (nj > 0) {
+    lr_tables_kernel<<<dim3(ceil_div(P, 128), nj), 128, 0, st>>>(lj, sc.wpack, P);
+    MOTIF_LAUNCHED("lr_tables_kernel");
+  }
+  return 0;
+}
+
+}  // namespace f16
+
+size_t decode_f16_workspace_bytes(int B, int H, int W, int HH, int WW) {
+  size_t bytes = 0;
+  f16::layout(B, H, W, HH, WW, nullptr, nullptr, &bytes);
+  return bytes;
+}
+
+int decode_f16(const motif_decode_t* a, cudaStream_t st) {
+  using namespace f16;
+  const motif_geom_t& g = a->geom;
+  MOTIF_REQUIRE(2ull * g.B * g.HH * g.WW < (1ull << 32), "decode: 2*B*HH*WW must fit 32 bits");
+  Scratch sc;
+  size_t need = 0;
+  layout(g.B, g.H, g.W, g.HH, g.WW, &sc, (char*)a->workspace, &need);
+  if (a->workspace_bytes < need) return fail(MOTIF_E_WORKSPACE, "decode: workspace %zu < %zu bytes", a->workspace_bytes, need);
+  if (a->n_begin == a->n_end) return 0;
+  MOTIF_REQUIRE(a->dbg_synth_in == nullptr, "decode: dbg_synth_in is only produced by precision fp32 / tf32x3 (f16x3 never forms the 198-channel input)");
+  const size_t qs = (size_t)g.HH * g.WW;
+  const int smem_i = (int)sizeof(SmemI) + 1024, smem_f = (int)sizeof(SmemF) + 1024, smem_s = (int)sizeof(SmemS) + 1024;
+  static bool attr_done = false;
+  static int n_sm = 148;
+  if (!attr_done) {
+    MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    MOTIF_CUDA(cudaFuncSetAttribute(synth_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+    int dev = 0;
+    MOTIF_CUDA(cudaGetDevice(&dev));
+    MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    attr_done = true;
+  }
+  if (int rc = prepare(a, sc, st)) return rc;
+  MOTIF_CUDA(cudaMemsetAsync(sc.side, 0, sizeof(float) * g.B * qs * 4, st));
+  MOTIF_CUDA(cudaMemsetAsync(sc.bin_count, 0, sizeof(int) * g.B * qs, st));
+  MOTIF_CUDA(cudaMemsetAsync(sc.spill, 0, sizeof(float) * g.B * qs * 64, st));
+  fill_kernel<<<148 * 8, 256, 0, st>>>(sc.zmax, 1.0f, (size_t)g.B * qs);
+  MOTIF_LAUNCHED("fill_kernel");
+  const int tiles128 = ceil_div((long long)qs, 128), units256 = ceil_div((long long)qs, 256);
+  const int grid128 = tiles128 < n_sm ? tiles128 : n_sm, grid256 = units256 < n_sm ? units256 : n_sm;
+  for (int b = 0; b < g.B; ++b) {
+    {
+      ProfScope prof("imnet_f16_kernel", st);
+      imnet_f16_kernel<<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc);
+      MOTIF_LAUNCHED("imnet_f16_kernel");
+    }
+    for (int n = a->n_begin; n < a->n_end; ++n) {
+      const float t = a->target_t[b * g.N + n];
+      {
+        ProfScope prof("flow_bin_f16_kernel", st);
+        flow_bin_f16_kernel<<<grid128, kThreads, smem_f, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
+        MOTIF_LAUNCHED("flow_bin_f16_kernel");
+      }
+      {
+        ProfScope prof("synth_f16_kernel", st);
+        synth_f16_kernel<<<grid256, kThreads, smem_s, st>>>(g, g.B, g.N, n, b, t, sc, a->rgb, a->dbg_pre0);
+        MOTIF_LAUNCHED("synth_f16_kernel");
+      }
+    }
+  }
+  return 0;
+}
+
+}  // namespace motif

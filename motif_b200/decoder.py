@@ -28,7 +28,8 @@ _SIREN_SHAPES = {
     "imnet": [(64, 66), (64, 64), (256, 64), (64, 256)],
     "synth_net": [(64, 198), (64, 64), (64, 64), (256, 64), (3, 256)],
 }
-PRECISIONS = {"tf32x3": 0, "fp32": 1}
+PRECISIONS = {"tf32x3": 0, "fp32": 1, "f16x3": 2}
+DEFAULT_PRECISION = "f16x3"
 
 
 def coord_sequence(n: int) -> torch.Tensor:
@@ -50,7 +51,7 @@ def _key(name: str, layer: int, last: bool, what: str) -> str:
 
 
 class SpaceTimeDecoder:
-    def __init__(self, params: Dict[str, torch.Tensor], device="cuda", precision: str = "tf32x3"):
+    def __init__(self, params: Dict[str, torch.Tensor], device="cuda", precision: str = DEFAULT_PRECISION):
         _lib.load()  # fail loudly when the CUDA library is missing
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {list(PRECISIONS)}")
@@ -78,7 +79,7 @@ class SpaceTimeDecoder:
         self._workspace = None
 
     @classmethod
-    def from_state_dict(cls, state_dict, device="cuda", precision="tf32x3"):
+    def from_state_dict(cls, state_dict, device="cuda", precision=DEFAULT_PRECISION):
         """Accepts a full ``LunaTokis`` ``state_dict`` (e.g. ``best.pth``, optional ``module.`` prefix)."""
         clean = {}
         for k, v in state_dict.items():
@@ -158,9 +159,12 @@ class SpaceTimeDecoder:
         return_flow: bool = True,
         debug_synth_in: bool = False,
         precision: Optional[str] = None,
+        debug_pre0: bool = False,
     ):
         """``Ours.py:659-858``.  Returns ``(rgb [N,B,3,HH,WW] in [0,1], flow_out [2BN,2,HH,WW] or None)``
-        (plus the ``[B*N,198,HH,WW]`` synth_net input when ``debug_synth_in``)."""
+        (plus the ``[B*N,198,HH,WW]`` synth_net input when ``debug_synth_in`` -- precisions ``fp32`` / ``tf32x3`` --
+        or the ``[B*N,64,HH,WW]`` layer-0 pre-activation of synth_net when ``debug_pre0`` -- precision ``f16x3``,
+        which never forms the 198-channel input)."""
         lib = _lib.load()
         for nm, t in (("feat", feat), ("flow_feat", flow_feat), ("residual", residual)):
             _lib.require_cuda_f32(nm, t, 4)
@@ -181,6 +185,7 @@ class SpaceTimeDecoder:
             rgb = torch.empty(N, B, 3, HH, WW, dtype=torch.float32, device=dev)
             flow_out = torch.empty(2 * B * N, 2, HH, WW, dtype=torch.float32, device=dev) if return_flow else None
             dbg = torch.zeros(B * N, 198, HH, WW, dtype=torch.float32, device=dev) if debug_synth_in else None
+            pre0 = torch.zeros(B * N, 64, HH, WW, dtype=torch.float32, device=dev) if debug_pre0 else None
             nbytes = lib.motif_decode_workspace_bytes(B, N, H, W, HH, WW)
             ws = self._get_workspace(nbytes)
             a = _lib.DecodeT()
@@ -194,10 +199,13 @@ class SpaceTimeDecoder:
             a.flow_out = flow_out.data_ptr() if flow_out is not None else None
             a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             a.dbg_synth_in = dbg.data_ptr() if dbg is not None else None
+            a.dbg_pre0 = pre0.data_ptr() if pre0 is not None else None
             a.n_begin, a.n_end = int(n0), int(n1)
             a.precision = PRECISIONS[precision or self.precision]
             rc = lib.motif_decode(ctypes.byref(a), _lib.current_stream_ptr(dev))
         _lib.check(rc, "motif_decode")
         if debug_synth_in:
             return rgb, flow_out, dbg
+        if debug_pre0:
+            return rgb, flow_out, pre0
         return rgb, flow_out

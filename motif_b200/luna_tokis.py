@@ -100,14 +100,14 @@ def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, tra
         dec = getattr(self, "_motif_decoder", None)
         sd_version = sum(p._version for p in self.parameters())
         if dec is None or dec.device != feat.device or self._motif_decoder_version != sd_version:
-            dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, precision=getattr(self, "_motif_precision", "tf32x3"))
+            dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, precision=getattr(self, "_motif_precision", "f16x3"))
             object.__setattr__(self, "_motif_decoder", dec)
             object.__setattr__(self, "_motif_decoder_version", sd_version)
         rgb, flow_out = dec.decode(feat.float(), flow_feat.float(), residual.float(), tt, (HH, WW))
     return rgb, flow_out, 0.0  # Ours.py:580, 858: flow_GT = 0 on the inference path, returned as (0 / 20.0) / (HH / H)
 
 
-def install(model, precision: str = "tf32x3"):
+def install(model, precision: str = "f16x3"):
     """Patch a reference ``LunaTokis`` instance in place and return it."""
     object.__setattr__(model, "_motif_precision", precision)
     model.fwarp = Softsplat()

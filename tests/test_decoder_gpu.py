@@ -53,7 +53,7 @@ def test_coord_sequence_host_matches_make_coord():
         assert torch.equal(coord_sequence(n), decoder_ref.make_coord((n,)).view(-1))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "f16x3"])
 @pytest.mark.parametrize("case", ["decoder_raft", "decoder_x4", "decoder_x3p5_b2"])
 def test_decoder_vs_reference_golden(case, precision):
     g = load_golden(case)
@@ -95,18 +95,69 @@ def test_decoder_stages_vs_oracle(precision):
     assert d_rgb < TOL and p > PSNR_MIN, (d_rgb, p)
 
 
-def test_timestamp_range_equals_full_decode():
+def test_f16x3_stages_vs_oracle():
+    """Default arithmetic (fp16 two-piece split, layer 0 folded through the splat): the synth_net layer-0
+    pre-activation -- the quantity that replaces the 198-channel input -- against the oracle's
+    synth_in @ W0^T + b0 (fp64), then the frames."""
+    gen = torch.Generator().manual_seed(3)
+    B, N, H, W, HH, WW = 1, 2, 12, 20, 42, 70
+    feat = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    ff = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    res = torch.randn(B, 64, H, W, generator=gen) * 0.3
+    tt = torch.tensor([[0.25, 0.8]])
+    params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
+    r_rgb, r_flow, inter = decoder_ref.decode(feat, ff, res, tt, HH, WW, params, return_intermediates=True)
+    dec = _decoder(params, "f16x3")
+    rgb, flow, pre0 = dec.decode(feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW), debug_pre0=True)
+    assert (flow.cpu() - r_flow).abs().max().item() < FLOW_TOL
+    w0 = params["synth_net.net.0.linear.weight"].double()
+    b0 = params["synth_net.net.0.linear.bias"].double()
+    ref_pre0 = torch.einsum("nchw,oc->nohw", inter["synth_in"].double(), w0) + b0.view(1, -1, 1, 1)
+    unstable = decoder_ref.count_unstable_mask(inter["flow_hr"], B, N)          # [N,B,1,HH,WW]
+    st = ~unstable.permute(1, 0, 2, 3, 4).reshape(B * N, 1, HH, WW)
+    d = (pre0.cpu().double() - ref_pre0).abs()
+    scale = ref_pre0.abs().max().item()
+    assert d[st.expand_as(d)].max().item() < 2e-5 * max(scale, 1.0), (d[st.expand_as(d)].max().item(), scale)
+    d_rgb, p, _ = _compare_frames(rgb.cpu(), r_rgb, r_flow, HH / H, B, N)
+    assert d_rgb < TOL and p > PSNR_MIN, (d_rgb, p)
+
+
+def test_f16x3_overfull_lists_spill():
+    """A contracting flow field piles > 16 contributions on some destinations: the spill accumulator path must
+    agree with the exact-fp32 CUDA-core path (which scatters with float atomics)."""
+    gen = torch.Generator().manual_seed(21)
+    B, H, W, HH, WW = 1, 8, 8, 64, 64
+    feat = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    ff = torch.randn(2 * B, 64, H, W, generator=gen) * 2.0      # strong, varied flows
+    res = torch.randn(B, 64, H, W, generator=gen) * 0.3
+    tt = torch.tensor([[0.5]])
+    params = decoder_ref.random_params(seed=9, **decoder_ref.REALISTIC)
+    a, fa = _decoder(params, "f16x3").decode(feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW))
+    r_rgb, r_flow, inter = decoder_ref.decode(feat, ff, res, tt, HH, WW, params, return_intermediates=True)
+    cnt = inter["synth_in"][:, 131] * 16.0
+    assert cnt.max().item() > 16, cnt.max().item()       # the case really overfills some lists
+    assert (fa.cpu() - r_flow).abs().max().item() < FLOW_TOL
+    unstable = decoder_ref.count_unstable_mask(inter["flow_hr"], B, 1).expand_as(r_rgb)
+    d = (a.cpu() - r_rgb).abs()
+    assert d[~unstable].max().item() < TOL, d[~unstable].max().item()
+    over = (cnt > 16).view(1, B, 1, HH, WW).expand_as(r_rgb) & ~unstable
+    assert over.any() and d[over].max().item() < TOL
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_timestamp_range_equals_full_decode(precision):
     """Sharding contract: decoding timestamps [a,b) gives the same frames as the full decode."""
     g = load_golden("decoder_x4")
     HH, WW = [int(v) for v in g["hr_size"]]
-    dec = _decoder(hot_params(g), "tf32x3")
+    dec = _decoder(hot_params(g), precision)
     args = (g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
     full, _ = dec.decode(*args)
     part, _ = dec.decode(*args, n_range=(1, 3))
     assert (part[1:3] - full[1:3]).abs().max().item() < 1e-5
 
 
-def test_vimeo_config_vs_oracle_and_psnr():
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_vimeo_config_vs_oracle_and_psnr(precision):
     """BASELINE config 0 (64x112 -> 256x448, t=0.5): whole hot path against the oracle."""
     gen = torch.Generator().manual_seed(11)
     H, W, HH, WW = 64, 112, 256, 448
@@ -116,14 +167,15 @@ def test_vimeo_config_vs_oracle_and_psnr():
     tt = torch.tensor([[0.5]])
     params = decoder_ref.random_params(seed=2, **decoder_ref.REALISTIC)
     r_rgb, r_flow = decoder_ref.decode(feat, ff, res, tt, HH, WW, params)
-    rgb, flow = _decoder(params, "tf32x3").decode(feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW))
+    rgb, flow = _decoder(params, precision).decode(feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW))
     assert (flow.cpu() - r_flow).abs().max().item() < FLOW_TOL
     d_rgb, p, _ = _compare_frames(rgb.cpu(), r_rgb, r_flow, HH / H, 1, 1)
     assert d_rgb < TOL and p > PSNR_MIN, (d_rgb, p)
 
 
-def test_adobe_full_size_properties():
-    """BASELINE config 1 size (180x320 -> 720x1280, 7 timestamps): tf32x3 tensor path vs the exact-fp32
+@pytest.mark.parametrize("precision", ["tf32x3", "f16x3"])
+def test_adobe_full_size_properties(precision):
+    """BASELINE config 1 size (180x320 -> 720x1280, 7 timestamps): tensor path vs the exact-fp32
     CUDA-core path on the device, finite and clamped output, determinism of shape/ordering."""
     gen = torch.Generator().manual_seed(7)
     H, W, HH, WW = 180, 320, 720, 1280
@@ -132,7 +184,7 @@ def test_adobe_full_size_properties():
     feat, ff, res = lat[0:2].contiguous().cuda(), lat[2:4].contiguous().cuda(), lat[4:5].contiguous().cuda()
     tt = torch.tensor([[k / 8 for k in range(1, 8)]])
     params = decoder_ref.random_params(seed=2, **decoder_ref.REALISTIC)
-    a, fa = _decoder(params, "tf32x3").decode(feat, ff, res, tt, (HH, WW))
+    a, fa = _decoder(params, precision).decode(feat, ff, res, tt, (HH, WW))
     b, fb = _decoder(params, "fp32").decode(feat, ff, res, tt, (HH, WW), n_range=(0, 2))
     assert a.shape == (7, 1, 3, HH, WW) and torch.isfinite(a).all()
     assert a.min().item() >= 0.0 and a.max().item() <= 1.0
