@@ -17,9 +17,9 @@
 //    listed rows with coalesced loads.  Lists that overflow fall back to float atomics on a spill accumulator.
 //  * All weight blocks of a kernel stay resident in shared memory (no per-tile weight streaming).
 //
-// One persistent CTA per SM, 12 warps: warp 0 loads the weight images once, warp 1 (one thread) issues every MMA,
-// warp 2 owns the TMEM allocation, warps 4-7 / 8-11 are the two 128-pixel tiles in flight (thread == pixel row ==
-// TMEM lane).  Per tile the 256 TMEM columns are [0,32) A_hi [32,64) A_lo [64,96) A2_hi [96,128) A2_lo
+// One persistent CTA per SM, 20 warps: warp 0 loads the weight images once, warps 1 and 3 (one thread each) issue
+// the MMAs of tile 0 / tile 1, warp 2 owns the TMEM allocation, warps 4-11 / 12-19 are the epilogue warps of the
+// two 128-pixel tiles in flight (two warps per TMEM lane quadrant, each owning half of the columns).  Per tile the 256 TMEM columns are [0,32) A_hi [32,64) A_lo [64,96) A2_hi [96,128) A2_lo
 // [128,192) D0 [192,256) D1 (fp16 pairs per A column).
 #include <cuda_fp16.h>
 
@@ -31,7 +31,8 @@ namespace f16 {
 
 using namespace tc;
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;            // 20 warps
+constexpr int kTileThreads = 256;        // epilogue threads per tile (8 warps)
 constexpr int kEpiWarp0 = 4;
 constexpr int kTileCols = 256;
 constexpr uint32_t kColA = 0, kColA2 = 64, kColD0 = 128;
@@ -216,6 +217,10 @@ __global__ void fill_kernel(float* p, float v, size_t n) {
 // ------------------------------------------------------------------------------------------------------
 // Shared-memory carve-up, barriers, MMA issue program
 // ------------------------------------------------------------------------------------------------------
+// 20 warps: 0 weight loader, 1 MMA issuer of tile 0, 2 TMEM allocator, 3 MMA issuer of tile 1,
+//           4-11 the 8 epilogue warps of tile 0, 12-19 those of tile 1.
+// An epilogue warp owns a TMEM lane quadrant (warp % 4: rows 32 q .. 32 q + 31 of the tile) and one HALF of the
+// columns / hidden units / corners / destinations of those rows, so every per-row stage is split over two warps.
 struct Bars {
   uint64_t w_full;
   uint64_t a_ready[2], a2_ready[2], a2_free[2];
@@ -238,6 +243,7 @@ struct Smem {
   unsigned char img[NIMG][kBlkBytes];  // must stay first (1024-byte aligned swizzle atoms)
   unsigned char extra[EXTRA_BYTES > 0 ? EXTRA_BYTES : 16];
   float consts[2048];
+  float4 xch[2][2][128];               // per tile, per half: partial output-layer sums of each row
   Bars bars;
 };
 
@@ -246,12 +252,12 @@ __device__ __forceinline__ unsigned char* align1024(unsigned char* p) { return p
 __device__ __forceinline__ void init_bars(Bars& b) {
   mbar_init(&b.w_full, 1);
   for (int t = 0; t < 2; ++t) {
-    mbar_init(&b.a_ready[t], 128);
-    mbar_init(&b.a2_ready[t], 128);
+    mbar_init(&b.a_ready[t], kTileThreads);
+    mbar_init(&b.a2_ready[t], kTileThreads);
     mbar_init(&b.a2_free[t], 1);
     for (int d = 0; d < 2; ++d) {
       mbar_init(&b.d_ready[t][d], 1);
-      mbar_init(&b.d_free[t][d], 128);
+      mbar_init(&b.d_free[t][d], kTileThreads);
     }
   }
   fence_mbar_init();
@@ -271,6 +277,8 @@ __device__ __forceinline__ void teardown(uint32_t tmem_base) {
   __syncthreads();
   if ((threadIdx.x >> 5) == 2) tmem_dealloc<512>(tmem_base);
 }
+// the 256 epilogue threads of one tile
+__device__ __forceinline__ void tile_sync(int tile) { asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(kTileThreads) : "memory"); }
 
 // warp 0, one lane: bring the kernel's weight images in with one bulk copy each
 __device__ __forceinline__ void load_images(unsigned char* dst, const unsigned char* wimg, int img0, int n_img, Bars& bars) {
@@ -278,13 +286,15 @@ __device__ __forceinline__ void load_images(unsigned char* dst, const unsigned c
   for (int i = 0; i < n_img; ++i) bulk_g2s(dst + (size_t)i * kBlkBytes, wimg + (size_t)(img0 + i) * kBlkBytes, kBlkBytes, &bars.w_full);
 }
 
-// warp 1, one lane.  a_tile_smem: base of the two shared-memory A tiles (hi 16 KB + lo 16 KB each) for a_src == 2.
+// One thread per tile issues that tile's MMAs in program order; the two tiles are independent pipelines that
+// share the tensor pipe.  a_tile_smem: this tile's shared-memory A operand (hi 16 KB then lo 16 KB) for a_src == 2.
 template <int NSTEPS>
-__device__ __forceinline__ void issuer_loop(Bars& bars, const unsigned char* img_base, const unsigned char* a_tile_smem, const Step (&prog)[NSTEPS],
-                                            int n_iters, uint32_t tmem_base) {
+__device__ __forceinline__ void issuer_loop(Bars& bars, int tile, const unsigned char* img_base, const unsigned char* a_tile_smem,
+                                            const Step (&prog)[NSTEPS], int n_iters, uint32_t tmem_base) {
   const uint32_t idesc = idesc_f16(128, 64);
-  uint32_t ph_a[2] = {0, 0}, ph_a2[2] = {0, 0};
-  uint32_t ph_dfree[2][2] = {{1, 1}, {1, 1}};  // buffers start free
+  uint32_t ph_a = 0, ph_a2 = 0;
+  uint32_t ph_dfree[2] = {1, 1};  // buffers start free
+  const uint32_t tbase = tmem_base + tile * kTileCols;
   mbar_wait(&bars.w_full, 0);
   for (int it = 0; it < n_iters; ++it) {
 #pragma unroll 1
@@ -292,78 +302,75 @@ __device__ __forceinline__ void issuer_loop(Bars& bars, const unsigned char* img
       const Step st = prog[s];
       const uint32_t bhi = smem_u32(img_base + (size_t)st.img * kBlkBytes);
       const uint32_t blo = bhi + kBlkHalf;
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile) {
-        const uint32_t tbase = tmem_base + tile * kTileCols;
-        if (st.wait_a == 1) {
-          mbar_wait(&bars.a_ready[tile], ph_a[tile]);
-          ph_a[tile] ^= 1;
-        } else if (st.wait_a == 2) {
-          mbar_wait(&bars.a2_ready[tile], ph_a2[tile]);
-          ph_a2[tile] ^= 1;
-        }
-        if (!st.acc) {
-          mbar_wait(&bars.d_free[tile][st.dbuf], ph_dfree[tile][st.dbuf]);
-          ph_dfree[tile][st.dbuf] ^= 1;
-        }
-        tc_fence_after();
-        const uint32_t dcol = tbase + kColD0 + 64 * st.dbuf;
-        bool acc = st.acc != 0;
-        if (st.a_src == 2) {
-          const uint32_t ahi = smem_u32(a_tile_smem + (size_t)tile * kBlkBytes * 2);  // tile: 128 rows x 128 B hi, then lo
-          const uint32_t alo = ahi + 2 * kBlkHalf;
-#pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t a = (term == 1) ? alo : ahi;
-            const uint32_t b = (term == 2) ? blo : bhi;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              mma_f16_ss(dcol, smem_desc_sw128(a + ks * 32), smem_desc_sw128(b + ks * 32), idesc, acc);
-              acc = true;
-            }
-          }
-        } else {
-          const uint32_t ahi = tbase + (st.a_src == 1 ? kColA2 : kColA);
-#pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t a = (term == 1) ? ahi + 32 : ahi;
-            const uint32_t b = (term == 2) ? blo : bhi;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              mma_f16_ts(dcol, a + ks * 8, smem_desc_sw128(b + ks * 32), idesc, acc);
-              acc = true;
-            }
-          }
-        }
-        if (st.commit_d) mma_commit(&bars.d_ready[tile][st.dbuf]);
-        if (st.commit_a2) mma_commit(&bars.a2_free[tile]);
+      if (st.wait_a == 1) {
+        mbar_wait(&bars.a_ready[tile], ph_a);
+        ph_a ^= 1;
+      } else if (st.wait_a == 2) {
+        mbar_wait(&bars.a2_ready[tile], ph_a2);
+        ph_a2 ^= 1;
       }
+      if (!st.acc) {
+        mbar_wait(&bars.d_free[tile][st.dbuf], ph_dfree[st.dbuf]);
+        ph_dfree[st.dbuf] ^= 1;
+      }
+      tc_fence_after();
+      const uint32_t dcol = tbase + kColD0 + 64 * st.dbuf;
+      bool acc = st.acc != 0;
+      if (st.a_src == 2) {
+        const uint32_t ahi = smem_u32(a_tile_smem);
+        const uint32_t alo = ahi + 2 * kBlkHalf;
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a = (term == 1) ? alo : ahi;
+          const uint32_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            mma_f16_ss(dcol, smem_desc_sw128(a + ks * 32), smem_desc_sw128(b + ks * 32), idesc, acc);
+            acc = true;
+          }
+        }
+      } else {
+        const uint32_t ahi = tbase + (st.a_src == 1 ? kColA2 : kColA);
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a = (term == 1) ? ahi + 32 : ahi;
+          const uint32_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            mma_f16_ts(dcol, a + ks * 8, smem_desc_sw128(b + ks * 32), idesc, acc);
+            acc = true;
+          }
+        }
+      }
+      if (st.commit_d) mma_commit(&bars.d_ready[tile][st.dbuf]);
+      if (st.commit_a2) mma_commit(&bars.a2_free[tile]);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Epilogue helpers (128 threads per tile; thread <-> TMEM lane)
+// Epilogue helpers (256 threads per tile; thread <-> (TMEM lane, column half))
 // ------------------------------------------------------------------------------------------------------
 struct Epi {
   Bars* bars;
-  int tile;
+  int tile, half, quad;
   uint32_t lane_addr;  // TMEM address of this thread's lane, column 0 of its tile
   uint32_t ph_dready[2];
   uint32_t ph_a2free;
 };
 
 __device__ __forceinline__ Epi make_epi(Bars& bars, uint32_t tmem_base) {
-  const int warp = threadIdx.x >> 5;
+  const int w = (threadIdx.x >> 5) - kEpiWarp0;
   Epi c;
   c.bars = &bars;
-  c.tile = (warp - kEpiWarp0) >> 2;
-  c.lane_addr = tmem_base + c.tile * kTileCols + ((uint32_t)((warp & 3) * 32) << 16);
+  c.tile = w >> 3;
+  c.half = (w >> 2) & 1;
+  c.quad = w & 3;
+  c.lane_addr = tmem_base + c.tile * kTileCols + ((uint32_t)(c.quad * 32) << 16);
   c.ph_dready[0] = c.ph_dready[1] = 0;
   c.ph_a2free = 1;  // A2 starts free
   return c;
 }
-__device__ __forceinline__ int epi_row() { return ((threadIdx.x >> 5) & 3) * 32 + (threadIdx.x & 31); }
 
 __device__ __forceinline__ void wait_d(Epi& c, int dbuf) {
   mbar_wait(&c.bars->d_ready[c.tile][dbuf], c.ph_dready[dbuf]);
@@ -378,6 +385,13 @@ __device__ __forceinline__ void publish(Epi& c, uint64_t* bar) {
   tmem_wait_st();
   tc_fence_before();
   mbar_arrive(bar);
+}
+// this thread's 32 columns of an accumulator block
+__device__ __forceinline__ void ld_half(Epi& c, int dbuf, uint32_t (&r)[32]) {
+  const uint32_t a = c.lane_addr + kColD0 + 64 * dbuf + 32 * c.half;
+  tmem_ld16p(a, r);
+  tmem_ld16p(a + 16, r + 16);
+  tmem_wait_ld();
 }
 
 // fp32 pair -> fp16 hi pair + fp16 lo pair (lo = fp16 of the exact fp32 remainder)
@@ -399,32 +413,42 @@ __device__ __forceinline__ void split_store16(uint32_t acol, const float (&v)[16
 
 // First layer from the LR table: v = sin(P0'[row] + e.x + e.y * rel_y + e.z * rel_x) (everything pre-scaled by 30)
 __device__ __forceinline__ void table_layer0(Epi& c, const float* __restrict__ p0row, const float4* __restrict__ e0, float rel_y, float rel_x) {
+  float4 p[8];
+  const float4* src = reinterpret_cast<const float4*>(p0row + 32 * c.half);
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
+  for (int j4 = 0; j4 < 8; ++j4) p[j4] = __ldg(src + j4);
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 16) {
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(p0row + c0) + j4);
-      const float pv[4] = {p.x, p.y, p.z, p.w};
+      const float4 pp = p[(c0 >> 2) + j4];
+      const float pv[4] = {pp.x, pp.y, pp.z, pp.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float4 e = e0[c0 + 4 * j4 + u];
+        const float4 e = e0[32 * c.half + c0 + 4 * j4 + u];
         v[4 * j4 + u] = __sinf(pv[u] + fmaf(e.z, rel_x, fmaf(e.y, rel_y, e.x)));
       }
     }
-    split_store16(c.lane_addr + kColA + c0 / 2, v);
+    split_store16(c.lane_addr + kColA + (32 * c.half + c0) / 2, v);
   }
   publish(c, &c.bars->a_ready[c.tile]);
 }
 
-// 64 -> 64 sine layer: D[dbuf] -> sin(s * D + cb) -> A.   s = 30 / weight scale, cb = 30 * bias (smem)
-__device__ __forceinline__ void sine_epilogue(Epi& c, int dbuf, float s, const float* __restrict__ cb) {
+// 64 -> 64 sine layer: D[dbuf] -> sin(s * D + cb) -> `acol` (A or A2).   s = 30 / weight scale, cb = 30 * bias (smem)
+__device__ __forceinline__ void sine_epilogue(Epi& c, int dbuf, float s, const float* __restrict__ cb, uint32_t acol, uint64_t* ready, bool wait_a2) {
   wait_d(c, dbuf);
-  uint32_t r[64];
-  tmem_ld64(c.lane_addr + kColD0 + 64 * dbuf, r);
+  uint32_t r[32];
+  ld_half(c, dbuf, r);
   release_d(c, dbuf);
+  if (wait_a2) {
+    mbar_wait(&c.bars->a2_free[c.tile], c.ph_a2free);
+    c.ph_a2free ^= 1;
+    tc_fence_after();
+  }
+  cb += 32 * c.half;
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
+  for (int c0 = 0; c0 < 32; c0 += 16) {
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
@@ -434,21 +458,22 @@ __device__ __forceinline__ void sine_epilogue(Epi& c, int dbuf, float s, const f
       v[4 * j4 + 2] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 2]), s, b.z));
       v[4 * j4 + 3] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 3]), s, b.w));
     }
-    split_store16(c.lane_addr + kColA + c0 / 2, v);
+    split_store16(c.lane_addr + acol + (32 * c.half + c0) / 2, v);
   }
-  publish(c, &c.bars->a_ready[c.tile]);
+  publish(c, ready);
 }
 
-// 64 hidden units of a 64 -> 256 sine layer followed by the 256 -> 3 linear layer on CUDA cores.
-// cw[j] = (30 * bias_j, w_out[0][j], w_out[1][j], w_out[2][j]) (smem)
+// This thread's 32 of the 64 hidden units of a 64 -> 256 sine-layer chunk, followed by the 256 -> 3 linear layer on
+// CUDA cores.  cw[j] = (30 * bias_j, w_out[0][j], w_out[1][j], w_out[2][j]) (smem, the chunk's 64 units)
 __device__ __forceinline__ void sine_out3_epilogue(Epi& c, int dbuf, float s, const float4* __restrict__ cw, float& o0, float& o1, float& o2) {
   wait_d(c, dbuf);
-  uint32_t r[64];
-  tmem_ld64(c.lane_addr + kColD0 + 64 * dbuf, r);
+  uint32_t r[32];
+  ld_half(c, dbuf, r);
   release_d(c, dbuf);
+  cw += 32 * c.half;
   float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
+  for (int j = 0; j < 32; ++j) {
     const float4 w = cw[j];
     const float v = __sinf(fmaf(__uint_as_float(r[j]), s, w.x));
     p0[j & 3] = fmaf(v, w.y, p0[j & 3]);
@@ -458,6 +483,17 @@ __device__ __forceinline__ void sine_out3_epilogue(Epi& c, int dbuf, float s, co
   o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
   o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
   o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+}
+
+// Sum of the two halves' partial outputs of one row; both halves get bit-identical totals (a + b == b + a).
+template <typename SM>
+__device__ __forceinline__ void combine_halves(SM& sm, Epi& c, int row, float& o0, float& o1, float& o2) {
+  sm.xch[c.tile][c.half][row] = make_float4(o0, o1, o2, 0.f);
+  tile_sync(c.tile);
+  const float4 other = sm.xch[c.tile][c.half ^ 1][row];
+  o0 += other.x;
+  o1 += other.y;
+  o2 += other.z;
 }
 
 // ======================================================================================================
@@ -501,8 +537,8 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 
   if (warp == 0) {
     if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgI1, 9, sm.bars);
-  } else if (warp == 1) {
-    if (lane == 0) issuer_loop(sm.bars, &sm.img[0][0], nullptr, kProgI, n_iters, tmem_base);
+  } else if (warp == 1 || warp == 3) {
+    if (lane == 0) issuer_loop(sm.bars, warp >> 1, &sm.img[0][0], nullptr, kProgI, n_iters, tmem_base);
   } else if (warp >= kEpiWarp0) {
     Epi c = make_epi(sm.bars, tmem_base);
     const int rb = c.tile * B + b;
@@ -510,46 +546,29 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
     const float s1 = sm.consts[640], s2 = sm.consts[641], s3 = sm.consts[642];
     for (int it = 0; it < n_iters; ++it) {
       const int tile_id = blockIdx.x + it * gridDim.x;
-      const int q = tile_id * 128 + epi_row();
+      const int q = tile_id * 128 + c.quad * 32 + lane;
       const bool live = q < qs;
       const int qc = live ? q : qs - 1;
       const Query qu = make_query(qc / g.WW, qc % g.WW, g);
       const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
       table_layer0(c, sc.p0i + lr * 64, e0, qu.rel_y, qu.rel_x);
-      sine_epilogue(c, 0, s1, sm.consts + 256);
+      sine_epilogue(c, 0, s1, sm.consts + 256, kColA, &sm.bars.a_ready[c.tile], false);
       // layer 2 chunk -> sine -> A2 (the K block of the output layer)
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        wait_d(c, 0);
-        uint32_t r[64];
-        tmem_ld64(c.lane_addr + kColD0, r);
-        release_d(c, 0);
-        mbar_wait(&sm.bars.a2_free[c.tile], c.ph_a2free);
-        c.ph_a2free ^= 1;
-        tc_fence_after();
-        const float* cb = sm.consts + 320 + 64 * ch;
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __sinf(fmaf(__uint_as_float(r[c0 + j]), s2, cb[c0 + j]));
-          split_store16(c.lane_addr + kColA2 + c0 / 2, v);
-        }
-        publish(c, &sm.bars.a2_ready[c.tile]);
-      }
+      for (int ch = 0; ch < 4; ++ch) sine_epilogue(c, 0, s2, sm.consts + 320 + 64 * ch, kColA2, &sm.bars.a2_ready[c.tile], true);
       // output: Y = s3 * D1 + 30 * bias' + 30 * W0b * feat[nearest]
       wait_d(c, 1);
       {
-        uint32_t r[64];
-        tmem_ld64(c.lane_addr + kColD0 + 64, r);
+        uint32_t r[32];
+        ld_half(c, 1, r);
         release_d(c, 1);
-        const float4* f4 = reinterpret_cast<const float4*>(sc.ftab + lr * 64);
-        float4* dst = reinterpret_cast<float4*>(sc.Y + ((size_t)rb * qs + qc) * 64);
+        const float4* f4 = reinterpret_cast<const float4*>(sc.ftab + lr * 64 + 32 * c.half);
+        float4* dst = reinterpret_cast<float4*>(sc.Y + ((size_t)rb * qs + qc) * 64 + 32 * c.half);
         if (live) {
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4) {
+          for (int j4 = 0; j4 < 8; ++j4) {
             const float4 f = __ldg(f4 + j4);
-            const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 576 + 4 * j4);
+            const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 576 + 32 * c.half + 4 * j4);
             dst[j4] = make_float4(fmaf(__uint_as_float(r[4 * j4 + 0]), s3, bb.x) + f.x, fmaf(__uint_as_float(r[4 * j4 + 1]), s3, bb.y) + f.y,
                                   fmaf(__uint_as_float(r[4 * j4 + 2]), s3, bb.z) + f.z, fmaf(__uint_as_float(r[4 * j4 + 3]), s3, bb.w) + f.w);
           }
@@ -598,8 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
 
   if (warp == 0) {
     if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgF1, 5, sm.bars);
-  } else if (warp == 1) {
-    if (lane == 0) issuer_loop(sm.bars, &sm.img[0][0], nullptr, kProgF, n_iters, tmem_base);
+  } else if (warp == 1 || warp == 3) {
+    if (lane == 0) issuer_loop(sm.bars, warp >> 1, &sm.img[0][0], nullptr, kProgF, n_iters, tmem_base);
   } else if (warp >= kEpiWarp0) {
     Epi c = make_epi(sm.bars, tmem_base);
     const int r = c.tile;
@@ -607,26 +626,29 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
     const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
     const float s1 = sm.consts[1348], s2 = sm.consts[1349];
+    const int row = c.quad * 32 + lane;
     for (int it = 0; it < n_iters; ++it) {
       const int tile_id = blockIdx.x + it * gridDim.x;
-      const int q = tile_id * 128 + epi_row();
+      const int q = tile_id * 128 + row;
       const bool live = q < qs;
       const int qc = live ? q : qs - 1;
       const int qy = qc / g.WW, qx = qc % g.WW;
       const Query qu = make_query(qy, qx, g);
       const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
       table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
-      sine_epilogue(c, 0, s1, sm.consts + 256);
-      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
+      sine_epilogue(c, 0, s1, sm.consts + 256, kColA, &sm.bars.a_ready[c.tile], false);
+      float dx = 0.f, dy = 0.f, zraw = 0.f;
+      if (c.half == 0) dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s2, cw + 64 * ch, dx, dy, zraw);
+      combine_halves(sm, c, row, dx, dy, zraw);
 
       // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
       const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
       const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
       const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
       const float e = expf(z);
-      if (live && flow_out != nullptr) {
+      if (live && flow_out != nullptr && c.half == 0) {
         float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
         fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
         fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
@@ -635,12 +657,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
       if (live && f.finite) {
         const uint32_t id = (uint32_t)((size_t)rb * qs + q);
         const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
+        // the two warps of a row take two corners each (half 0: north, half 1: south)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = 2 * c.half + kk;
           const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
           if ((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH)) continue;
           const size_t d = (size_t)b * qs + (size_t)cy * g.WW + cx;
-          const float wk = f.w[k];
+          const float wk = kk == 0 ? (c.half ? f.w[2] : f.w[0]) : (c.half ? f.w[3] : f.w[1]);
           const float we = __fmul_rn(e, wk);
           const int slot = atomicAdd(sc.bin_count + d, 1);
           if (slot < kSlots) {
@@ -676,11 +700,12 @@ __constant__ Step kProgS[kNumStepsS] = {
     {4, 0, 0, 0, 0, 1, 0},
     {5, 1, 0, 0, 0, 1, 0},
 };
+constexpr int kGatherDests = 16;  // destinations per epilogue warp
 struct WarpStage {
-  uint2 ent[32][kSlots];  // list entries of the warp's 32 destinations
-  float4 par[32][2];      // (1/wz, dx', dy', zmax), (count/16, wz/count, lr index bits, count bits)
+  uint2 ent[kGatherDests][kSlots];  // list entries of the warp's destinations
+  float4 par[kGatherDests][2];      // (1/wz, dx', dy', zmax), (count/16, wz/count, lr index bits, count bits)
 };
-constexpr int kSynthExtra = 2 * 2 * kBlkBytes + 8 * (int)sizeof(WarpStage);  // two A tiles (hi+lo, 128 rows) + staging
+constexpr int kSynthExtra = 2 * 2 * kBlkBytes + 16 * (int)sizeof(WarpStage);  // two A tiles (hi+lo, 128 rows) + staging
 using SmemS = Smem<6, kSynthExtra>;
 
 // consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) float4 per hidden unit (30 b3, w4[0], w4[1], w4[2])  [1152,1155) b4
@@ -710,8 +735,8 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
 
   if (warp == 0) {
     if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgS1, 6, sm.bars);
-  } else if (warp == 1) {
-    if (lane == 0) issuer_loop(sm.bars, &sm.img[0][0], a_tiles, kProgS, n_iters, tmem_base);
+  } else if (warp == 1 || warp == 3) {
+    if (lane == 0) issuer_loop(sm.bars, warp >> 1, &sm.img[0][0], a_tiles + (size_t)(warp >> 1) * 2 * kBlkBytes, kProgS, n_iters, tmem_base);
   } else if (warp >= kEpiWarp0) {
     Epi c = make_epi(sm.bars, tmem_base);
     WarpStage& ws = reinterpret_cast<WarpStage*>(sm.extra + 2 * 2 * kBlkBytes)[warp - kEpiWarp0];
@@ -720,6 +745,7 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
     const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
     const int bn = b * N + n;
+    const int row = c.quad * 32 + lane;
     // rank-1 input weights of this lane's two channels (2 lane, 2 lane + 1), pre-scaled by 30:
     // s_e0[ch] = (bias [in rtab], w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t, 0)
     float rk[2][5], ct[2];
@@ -732,14 +758,70 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
     }
     const float2* Y2 = reinterpret_cast<const float2*>(sc.Y);
     const float2* R2 = reinterpret_cast<const float2*>(sc.rtab);
+
+    // issue the row loads of destination j (first 8 list entries + its residual-table row)
+    auto issue = [&](int j, float2 (&y)[8], float2& rr) {
+      const float4 pb = ws.par[j][1];
+      const int cnt = min(__float_as_int(pb.w), 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t id = ws.ent[j][k].x;
+        y[k] = k < cnt ? __ldg(Y2 + (size_t)id * 32 + lane) : make_float2(0.f, 0.f);
+      }
+      rr = __ldg(R2 + ((size_t)b * P + __float_as_int(pb.z)) * 32 + lane);
+    };
+    // blend, layer-0 pre-activation, sine, split, store into the shared-memory A tile
+    auto finish = [&](int j, int q_w, const float2 (&y)[8], const float2 rr) {
+      const float4 pa = ws.par[j][0], pb = ws.par[j][1];
+      const int cnt_i = __float_as_int(pb.w);
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float we = k < cnt_i ? __uint_as_float(ws.ent[j][k].y) : 0.0f;
+        acc.x = fmaf(we, y[k].x, acc.x);
+        acc.y = fmaf(we, y[k].y, acc.y);
+      }
+      const int cnt = min(cnt_i, kSlots);
+      for (int k = 8; k < cnt; ++k) {  // long lists (rare)
+        const uint2 en = ws.ent[j][k];
+        const float2 v = __ldg(Y2 + (size_t)en.x * 32 + lane);
+        acc.x = fmaf(__uint_as_float(en.y), v.x, acc.x);
+        acc.y = fmaf(__uint_as_float(en.y), v.y, acc.y);
+      }
+      const int dq = q_w + j;
+      if (cnt_i > kSlots) {  // spilled contributions of an overfull list
+        float2* sp = reinterpret_cast<float2*>(sc.spill + ((size_t)b * qs + dq) * 64) + lane;
+        const float2 v = *sp;
+        acc.x += v.x;
+        acc.y += v.y;
+        *sp = make_float2(0.f, 0.f);
+      }
+      float pre[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float lin = fmaf(rk[u][0], pa.y, fmaf(rk[u][1], pa.z, fmaf(rk[u][2], pa.w, fmaf(rk[u][3], pb.x, fmaf(rk[u][4], pb.y, ct[u])))));
+        pre[u] = fmaf(u == 0 ? acc.x : acc.y, pa.x, (u == 0 ? rr.x : rr.y) + lin);
+      }
+      if (dbg_pre0 != nullptr && cnt_i >= 0) {
+        dbg_pre0[((size_t)bn * 64 + 2 * lane) * qs + dq] = pre[0] * (1.0f / kOmega);
+        dbg_pre0[((size_t)bn * 64 + 2 * lane + 1) * qs + dq] = pre[1] * (1.0f / kOmega);
+      }
+      uint32_t hi, lo;
+      split_pair(__sinf(pre[0]), __sinf(pre[1]), hi, lo);
+      const uint32_t off = sw128_offset_h(c.quad * 32 + c.half * kGatherDests + j, 2 * lane);
+      *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
+      *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
+    };
+
     for (int it = 0; it < n_iters; ++it) {
       const int unit = blockIdx.x + it * gridDim.x;
-      const int q_w = unit * 256 + c.tile * 128 + (warp & 3) * 32;  // first destination of this warp
-      const int q = q_w + lane;
-      const bool live = q < qs;
-      const int qc = live ? q : qs - 1;
+      const int q_t = unit * 256 + c.tile * 128;                       // first destination of the tile
+      const int q_w = q_t + c.quad * 32 + c.half * kGatherDests;       // first destination gathered by this warp
       // ---- per-destination scalars (Ours.py:813-814, 826-829, 834), re-arm the accumulators ----
-      {
+      if (lane < kGatherDests) {
+        const int q = q_w + lane;
+        const bool live = q < qs;
+        const int qc = live ? q : qs - 1;
         const size_t d = (size_t)b * qs + qc;
         float4 side = make_float4(0.f, 0.f, 0.f, 0.f);
         float zm = 1.0f;
@@ -762,75 +844,43 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
         const int lr = qu.iy * g.W + qu.ix;
         ws.par[lane][0] = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
         ws.par[lane][1] = make_float4(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_), __int_as_float(lr), __int_as_float(live ? cnt_i : -1));
-        // the 32 lists of this warp are contiguous: copy them with coalesced 16-byte loads
+      }
+      {
+        // the 16 lists of this warp are contiguous: copy them with coalesced 16-byte loads
         const uint4* src = reinterpret_cast<const uint4*>(sc.bin_ent + ((size_t)b * qs + q_w) * kSlots);
         uint4* dst = reinterpret_cast<uint4*>(&ws.ent[0][0]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kGatherDests / 4; ++i) {
           const int idx = i * 32 + lane;
           dst[idx] = (q_w + (idx >> 3) < qs) ? __ldg(src + idx) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
       __syncwarp();
-      // ---- cooperative gather: one destination at a time, lane = channel pair ----
+      // ---- cooperative gather: one destination at a time, lane = channel pair, next destination's rows in flight ----
+      {
+        float2 ya[8], yb[8], ra, rb2;
+        issue(0, ya, ra);
 #pragma unroll 1
-      for (int j = 0; j < 32; ++j) {
-        const float4 pa = ws.par[j][0], pb = ws.par[j][1];
-        const int cnt_i = __float_as_int(pb.w);
-        const int cnt = min(cnt_i, kSlots);
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll 1
-        for (int k0 = 0; k0 < cnt; k0 += 8) {
-          float2 y[8];
-          float we[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint2 en = ws.ent[j][(k0 + k) & (kSlots - 1)];
-            const bool on = k0 + k < cnt;
-            we[k] = on ? __uint_as_float(en.y) : 0.0f;
-            y[k] = on ? __ldg(Y2 + (size_t)en.x * 32 + lane) : make_float2(0.f, 0.f);
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            acc.x = fmaf(we[k], y[k].x, acc.x);
-            acc.y = fmaf(we[k], y[k].y, acc.y);
-          }
+        for (int j = 0; j < kGatherDests; j += 2) {
+          issue(j + 1, yb, rb2);
+          finish(j, q_w, ya, ra);
+          if (j + 2 < kGatherDests) issue(j + 2, ya, ra);
+          finish(j + 1, q_w, yb, rb2);
         }
-        const int dq = q_w + j;
-        if (cnt_i > kSlots) {  // spilled contributions of an overfull list
-          float2* sp = reinterpret_cast<float2*>(sc.spill + ((size_t)b * qs + dq) * 64) + lane;
-          const float2 v = *sp;
-          acc.x += v.x;
-          acc.y += v.y;
-          *sp = make_float2(0.f, 0.f);
-        }
-        const float2 rr = __ldg(R2 + ((size_t)b * P + __float_as_int(pb.z)) * 32 + lane);
-        float pre[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float lin = fmaf(rk[u][0], pa.y, fmaf(rk[u][1], pa.z, fmaf(rk[u][2], pa.w, fmaf(rk[u][3], pb.x, fmaf(rk[u][4], pb.y, ct[u])))));
-          pre[u] = fmaf(u == 0 ? acc.x : acc.y, pa.x, (u == 0 ? rr.x : rr.y) + lin);
-        }
-        if (dbg_pre0 != nullptr && cnt_i >= 0) {
-          dbg_pre0[((size_t)bn * 64 + 2 * lane) * qs + dq] = pre[0] * (1.0f / kOmega);
-          dbg_pre0[((size_t)bn * 64 + 2 * lane + 1) * qs + dq] = pre[1] * (1.0f / kOmega);
-        }
-        uint32_t hi, lo;
-        split_pair(__sinf(pre[0]), __sinf(pre[1]), hi, lo);
-        const int row = (warp & 3) * 32 + j;
-        const uint32_t off = sw128_offset_h(row, 2 * lane);
-        *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
-        *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
       }
+      __syncwarp();
       fence_proxy_async_smem();
       mbar_arrive(&sm.bars.a_ready[c.tile]);
-      // ---- layers 1..3 and the output layer, thread per pixel ----
-      sine_epilogue(c, 0, s1, sm.consts);
-      sine_epilogue(c, 0, s2, sm.consts + 64);
-      float o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
+      // ---- layers 1..3 and the output layer: thread = (pixel row, column half) ----
+      sine_epilogue(c, 0, s1, sm.consts, kColA, &sm.bars.a_ready[c.tile], false);
+      sine_epilogue(c, 0, s2, sm.consts + 64, kColA, &sm.bars.a_ready[c.tile], false);
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+      if (c.half == 0) o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s3, cw + 64 * ch, o0, o1, o2);
-      if (live) {
+      combine_halves(sm, c, row, o0, o1, o2);
+      const int q = q_t + row;
+      if (q < qs && c.half == 0) {
         float* out = rgb + ((size_t)(n * B + b) * 3) * qs + q;
         out[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
         out[(size_t)qs] = fminf(fmaxf(o1, 0.0f), 1.0f);
