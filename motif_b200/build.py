@@ -50,6 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
+        if os.environ.get("MOTIF_TRACE"):
+            cmd.insert(1, "-DMOTIF_TRACE")
         if verbose:
             cmd += ["-Xptxas", "-v"]
             print(" ".join(cmd))

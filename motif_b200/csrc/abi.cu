@@ -86,4 +86,7 @@ extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
   }
 }
 
-extern "C" int motif_tc_set_trace(long long* buf, int capacity) { return tc_set_trace(buf, capacity); }
+extern "C" int motif_tc_set_trace(long long* buf, int capacity) {
+  if (int rc = tc_set_trace(buf, capacity)) return rc;
+  return f16_set_trace(buf, capacity);
+}

@@ -103,5 +103,6 @@ size_t decode_f16_workspace_bytes(int B, int H, int W, int HH, int WW);
 int check_decode(const motif_decode_t* a);
 size_t tc_image_bytes();
 int tc_set_trace(long long* buf, int capacity);
+int f16_set_trace(long long* buf, int capacity);
 
 }  // namespace motif

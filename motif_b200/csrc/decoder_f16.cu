@@ -22,6 +22,7 @@
 // two 128-pixel tiles in flight (two warps per TMEM lane quadrant, each owning half of the columns).  Per tile the 256 TMEM columns are [0,32) A_hi [32,64) A_lo [64,96) A2_hi [96,128) A2_lo
 // [128,192) D0 [192,256) D1 (fp16 pairs per A column).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
@@ -40,6 +41,49 @@ constexpr int kSlots = 16;                 // list entries per destination pixel
 constexpr int kBlkHalf = 64 * 64 * 2;      // one fp16 64x64 block (hi or lo)
 constexpr int kBlkBytes = 2 * kBlkHalf;    // hi image followed by lo image
 constexpr float kOmega = 30.0f;            // SIREN.py:45
+
+// Optional pipeline trace (tuning builds only, -DMOTIF_TRACE): CTA 0 records (event id, clock64) pairs into the
+// buffer installed with motif_tc_set_trace().  Event ids: epilogue lane 0 of (quad 0, half 0) of a tile = 100 * tile + k,
+// MMA issuer of a tile = 1000 + 100 * tile + step (waits done) and 2000 + 100 * tile + step (block issued).
+#ifdef MOTIF_TRACE
+__device__ long long* g_trace16 = nullptr;
+__device__ int g_trace16_cap = 0;
+__device__ int g_trace16_n = 0;
+__device__ int g_trace16_on = 0;  // set by the host before each launch: 1 when this kernel is the traced one
+// four recording threads, each with a private quarter of the buffer and a private counter in shared memory
+// (no atomics, no round trips: a clock read and a fire-and-forget store)
+__device__ __noinline__ int* trace_counters() {
+  __shared__ int cnt[4];
+  return cnt;
+}
+__device__ __forceinline__ void trace(int region, int id) {
+  int* cnt = trace_counters();
+  if (g_trace16 != nullptr && blockIdx.x == 0 && g_trace16_on) {
+    const int quarter = g_trace16_cap >> 2;
+    const int i = cnt[region]++;
+    if (i < quarter) {
+      g_trace16[2 * (region * quarter + i)] = id;
+      g_trace16[2 * (region * quarter + i) + 1] = clock64();
+    }
+  }
+}
+#define TRACE(id) do { if ((threadIdx.x & 31) == 0) trace(((id) / 100) & 1, id); } while (0)
+#define TRACE_EPI(c, k) do { if ((c).quad == 0 && (c).half == 0 && (threadIdx.x & 31) == 0) trace(2 + (c).tile, 100 * (c).tile + (k)); } while (0)
+#else
+#define TRACE(id) do { } while (0)
+#define TRACE_EPI(c, k) do { } while (0)
+#endif
+// which kernel the trace build records: MOTIF_TRACE_KERNEL = 0 imnet, 1 flow_bin (default), 2 synth
+static int trace_select(int kernel, cudaStream_t st) {
+#ifdef MOTIF_TRACE
+  const char* e = getenv("MOTIF_TRACE_KERNEL");
+  const int on = (e ? atoi(e) : 1) == kernel;
+  MOTIF_CUDA(cudaMemcpyToSymbolAsync(g_trace16_on, &on, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+#else
+  (void)kernel, (void)st;
+#endif
+  return 0;
+}
 
 // weight block images (program order per kernel) and per-layer scale slots
 enum { kImgF1 = 0, kImgF2 = 1, kImgI1 = 5, kImgI2 = 6, kImgI3 = 10, kImgS1 = 14, kImgS2 = 15, kImgS3 = 16, kNumImg = 20 };
@@ -266,10 +310,14 @@ __device__ __forceinline__ void init_bars(Bars& b) {
 __device__ __forceinline__ uint32_t setup(Bars& bars) {
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) init_bars(bars);
+#ifdef MOTIF_TRACE
+  if (threadIdx.x < 4) trace_counters()[threadIdx.x] = 0;
+#endif
   if (warp == 2) tmem_alloc<512>(&bars.tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (bars.tmem_base != 0) __trap();  // the only CTA of the SM allocates all 512 columns: the issuers use immediates
   return bars.tmem_base;
 }
 __device__ __forceinline__ void teardown(uint32_t tmem_base) {
@@ -286,22 +334,40 @@ __device__ __forceinline__ void load_images(unsigned char* dst, const unsigned c
   for (int i = 0; i < n_img; ++i) bulk_g2s(dst + (size_t)i * kBlkBytes, wimg + (size_t)(img0 + i) * kBlkBytes, kBlkBytes, &bars.w_full);
 }
 
-// One thread per tile issues that tile's MMAs in program order; the two tiles are independent pipelines that
-// share the tensor pipe.  a_tile_smem: this tile's shared-memory A operand (hi 16 KB then lo 16 KB) for a_src == 2.
-template <int NSTEPS>
-__device__ __forceinline__ void issuer_loop(Bars& bars, int tile, const unsigned char* img_base, const unsigned char* a_tile_smem,
-                                            const Step (&prog)[NSTEPS], int n_iters, uint32_t tmem_base) {
-  const uint32_t idesc = idesc_f16(128, 64);
+// One warp per tile walks that tile's MMA program; the two tiles are independent pipelines that share the tensor
+// pipe.  The WHOLE warp executes the loop (waits included) and one elected lane issues, so that every operand of the
+// MMA stream -- TMEM columns, shared-memory descriptors, the step program -- lives in uniform registers: a
+// single-lane branch around the loop costs a register-to-uniform waterfall (~100 cycles) per MMA, which made the
+// issue rate, not the tensor pipe, the critical path (profiles/r1_trace_*.txt).  The CTA owns all 512 TMEM columns,
+// so its allocation starts at column 0 (checked in setup()) and the TMEM operands are immediates.
+// a_tile_smem: this tile's shared-memory A operand (hi 16 KB then lo 16 KB) for a_src == 2.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(p));
+  return p != 0;
+}
+
+template <int tile, int NSTEPS>
+__device__ __forceinline__ void issuer_loop(Bars& bars, const unsigned char* img_base, const unsigned char* a_tile_smem,
+                                            const Step (&prog)[NSTEPS], int n_iters) {
+  constexpr uint32_t idesc = idesc_f16(128, 64);
   uint32_t ph_a = 0, ph_a2 = 0;
   uint32_t ph_dfree[2] = {1, 1};  // buffers start free
-  const uint32_t tbase = tmem_base + tile * kTileCols;
+  const uint32_t tbase = tile * kTileCols;
+  const uint64_t img_desc = smem_desc_sw128(smem_u32(img_base));
+  const uint64_t a_desc = smem_desc_sw128(smem_u32(a_tile_smem));
   mbar_wait(&bars.w_full, 0);
   for (int it = 0; it < n_iters; ++it) {
 #pragma unroll 1
     for (int s = 0; s < NSTEPS; ++s) {
       const Step st = prog[s];
-      const uint32_t bhi = smem_u32(img_base + (size_t)st.img * kBlkBytes);
-      const uint32_t blo = bhi + kBlkHalf;
+      // descriptors differ only in the 14-bit start-address field (units of 16 bytes): no carry out of it
+      const uint64_t bhi = img_desc + (uint64_t)(st.img * (kBlkBytes >> 4));
+      const uint64_t blo = bhi + (kBlkHalf >> 4);
       if (st.wait_a == 1) {
         mbar_wait(&bars.a_ready[tile], ph_a);
         ph_a ^= 1;
@@ -314,36 +380,40 @@ __device__ __forceinline__ void issuer_loop(Bars& bars, int tile, const unsigned
         ph_dfree[st.dbuf] ^= 1;
       }
       tc_fence_after();
+      TRACE(1000 + 100 * tile + s);
       const uint32_t dcol = tbase + kColD0 + 64 * st.dbuf;
-      bool acc = st.acc != 0;
-      if (st.a_src == 2) {
-        const uint32_t ahi = smem_u32(a_tile_smem);
-        const uint32_t alo = ahi + 2 * kBlkHalf;
+      if (elect_one()) {
+        bool acc = st.acc != 0;
+        if (st.a_src == 2) {
+          const uint64_t ahi = a_desc, alo = a_desc + ((2 * kBlkHalf) >> 4);
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a = (term == 1) ? alo : ahi;
-          const uint32_t b = (term == 2) ? blo : bhi;
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t a = (term == 1) ? alo : ahi;
+            const uint64_t b = (term == 2) ? blo : bhi;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mma_f16_ss(dcol, smem_desc_sw128(a + ks * 32), smem_desc_sw128(b + ks * 32), idesc, acc);
-            acc = true;
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_f16_ss(dcol, a + 2 * ks, b + 2 * ks, idesc, acc);
+              acc = true;
+            }
+          }
+        } else {
+          const uint32_t ahi = tbase + (st.a_src == 1 ? kColA2 : kColA);
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            const uint32_t a = (term == 1) ? ahi + 32 : ahi;
+            const uint64_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_f16_ts(dcol, a + ks * 8, b + 2 * ks, idesc, acc);
+              acc = true;
+            }
           }
         }
-      } else {
-        const uint32_t ahi = tbase + (st.a_src == 1 ? kColA2 : kColA);
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a = (term == 1) ? ahi + 32 : ahi;
-          const uint32_t b = (term == 2) ? blo : bhi;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            mma_f16_ts(dcol, a + ks * 8, smem_desc_sw128(b + ks * 32), idesc, acc);
-            acc = true;
-          }
-        }
+        if (st.commit_d) mma_commit(&bars.d_ready[tile][st.dbuf]);
+        if (st.commit_a2) mma_commit(&bars.a2_free[tile]);
       }
-      if (st.commit_d) mma_commit(&bars.d_ready[tile][st.dbuf]);
-      if (st.commit_a2) mma_commit(&bars.a2_free[tile]);
+      __syncwarp();
+      TRACE(2000 + 100 * tile + s);
     }
   }
 }
@@ -376,6 +446,7 @@ __device__ __forceinline__ void wait_d(Epi& c, int dbuf) {
   mbar_wait(&c.bars->d_ready[c.tile][dbuf], c.ph_dready[dbuf]);
   c.ph_dready[dbuf] ^= 1;
   tc_fence_after();
+  TRACE_EPI(c, 10 + dbuf);
 }
 __device__ __forceinline__ void release_d(Epi& c, int dbuf) {
   tc_fence_before();
@@ -385,6 +456,7 @@ __device__ __forceinline__ void publish(Epi& c, uint64_t* bar) {
   tmem_wait_st();
   tc_fence_before();
   mbar_arrive(bar);
+  TRACE_EPI(c, 20);
 }
 // this thread's 32 columns of an accumulator block
 __device__ __forceinline__ void ld_half(Epi& c, int dbuf, uint32_t (&r)[32]) {
@@ -537,8 +609,10 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 
   if (warp == 0) {
     if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgI1, 9, sm.bars);
-  } else if (warp == 1 || warp == 3) {
-    if (lane == 0) issuer_loop(sm.bars, warp >> 1, &sm.img[0][0], nullptr, kProgI, n_iters, tmem_base);
+  } else if (warp == 1) {
+    issuer_loop<0>(sm.bars, &sm.img[0][0], &sm.img[0][0], kProgI, n_iters);
+  } else if (warp == 3) {
+    issuer_loop<1>(sm.bars, &sm.img[0][0], &sm.img[0][0], kProgI, n_iters);
   } else if (warp >= kEpiWarp0) {
     Epi c = make_epi(sm.bars, tmem_base);
     const int rb = c.tile * B + b;
@@ -617,8 +691,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
 
   if (warp == 0) {
     if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgF1, 5, sm.bars);
-  } else if (warp == 1 || warp == 3) {
-    if (lane == 0) issuer_loop(sm.bars, warp >> 1, &sm.img[0][0], nullptr, kProgF, n_iters, tmem_base);
+  } else if (warp == 1) {
+    issuer_loop<0>(sm.bars, &sm.img[0][0], &sm.img[0][0], kProgF, n_iters);
+  } else if (warp == 3) {
+    issuer_loop<1>(sm.bars, &sm.img[0][0], &sm.img[0][0], kProgF, n_iters);
   } else if (warp >= kEpiWarp0) {
     Epi c = make_epi(sm.bars, tmem_base);
     const int r = c.tile;
@@ -628,6 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
     const float s1 = sm.consts[1348], s2 = sm.consts[1349];
     const int row = c.quad * 32 + lane;
     for (int it = 0; it < n_iters; ++it) {
+      TRACE_EPI(c, 1);
       const int tile_id = blockIdx.x + it * gridDim.x;
       const int q = tile_id * 128 + row;
       const bool live = q < qs;
@@ -641,7 +718,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
       if (c.half == 0) dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s2, cw + 64 * ch, dx, dy, zraw);
+      TRACE_EPI(c, 2);
       combine_halves(sm, c, row, dx, dy, zraw);
+      TRACE_EPI(c, 3);
 
       // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
       const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
@@ -683,6 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
           if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
         }
       }
+      TRACE_EPI(c, 4);
     }
   }
   teardown(tmem_base);
@@ -735,8 +815,10 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
 
   if (warp == 0) {
     if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgS1, 6, sm.bars);
-  } else if (warp == 1 || warp == 3) {
-    if (lane == 0) issuer_loop(sm.bars, warp >> 1, &sm.img[0][0], a_tiles + (size_t)(warp >> 1) * 2 * kBlkBytes, kProgS, n_iters, tmem_base);
+  } else if (warp == 1) {
+    issuer_loop<0>(sm.bars, &sm.img[0][0], a_tiles, kProgS, n_iters);
+  } else if (warp == 3) {
+    issuer_loop<1>(sm.bars, &sm.img[0][0], a_tiles + 2 * kBlkBytes, kProgS, n_iters);
   } else if (warp >= kEpiWarp0) {
     Epi c = make_epi(sm.bars, tmem_base);
     WarpStage& ws = reinterpret_cast<WarpStage*>(sm.extra + 2 * 2 * kBlkBytes)[warp - kEpiWarp0];
@@ -814,6 +896,7 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
     };
 
     for (int it = 0; it < n_iters; ++it) {
+      TRACE_EPI(c, 1);
       const int unit = blockIdx.x + it * gridDim.x;
       const int q_t = unit * 256 + c.tile * 128;                       // first destination of the tile
       const int q_w = q_t + c.quad * 32 + c.half * kGatherDests;       // first destination gathered by this warp
@@ -856,6 +939,7 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
         }
       }
       __syncwarp();
+      TRACE_EPI(c, 5);
       // ---- cooperative gather: one destination at a time, lane = channel pair, next destination's rows in flight ----
       {
         float2 ya[8], yb[8], ra, rb2;
@@ -871,6 +955,7 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
       __syncwarp();
       fence_proxy_async_smem();
       mbar_arrive(&sm.bars.a_ready[c.tile]);
+      TRACE_EPI(c, 6);
       // ---- layers 1..3 and the output layer: thread = (pixel row, column half) ----
       sine_epilogue(c, 0, s1, sm.consts, kColA, &sm.bars.a_ready[c.tile], false);
       sine_epilogue(c, 0, s2, sm.consts + 64, kColA, &sm.bars.a_ready[c.tile], false);
@@ -878,6 +963,7 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
       if (c.half == 0) o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s3, cw + 64 * ch, o0, o1, o2);
+      TRACE_EPI(c, 2);
       combine_halves(sm, c, row, o0, o1, o2);
       const int q = q_t + row;
       if (q < qs && c.half == 0) {
@@ -955,6 +1041,18 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
 
 }  // namespace f16
 
+int f16_set_trace(long long* buf, int capacity) {
+#ifdef MOTIF_TRACE
+  int zero = 0;
+  MOTIF_CUDA(cudaMemcpyToSymbol(f16::g_trace16, &buf, sizeof(buf)));
+  MOTIF_CUDA(cudaMemcpyToSymbol(f16::g_trace16_cap, &capacity, sizeof(int)));
+  MOTIF_CUDA(cudaMemcpyToSymbol(f16::g_trace16_n, &zero, sizeof(int)));
+#else
+  (void)buf, (void)capacity;
+#endif
+  return 0;
+}
+
 size_t decode_f16_workspace_bytes(int B, int H, int W, int HH, int WW) {
   size_t bytes = 0;
   f16::layout(B, H, W, HH, WW, nullptr, nullptr, &bytes);
@@ -994,6 +1092,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   const int grid128 = tiles128 < n_sm ? tiles128 : n_sm, grid256 = units256 < n_sm ? units256 : n_sm;
   for (int b = 0; b < g.B; ++b) {
     {
+      if (int rc = trace_select(0, st)) return rc;
       ProfScope prof("imnet_f16_kernel", st);
       imnet_f16_kernel<<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc);
       MOTIF_LAUNCHED("imnet_f16_kernel");
@@ -1001,11 +1100,13 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     for (int n = a->n_begin; n < a->n_end; ++n) {
       const float t = a->target_t[b * g.N + n];
       {
+        if (int rc = trace_select(1, st)) return rc;
         ProfScope prof("flow_bin_f16_kernel", st);
         flow_bin_f16_kernel<<<grid128, kThreads, smem_f, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
         MOTIF_LAUNCHED("flow_bin_f16_kernel");
       }
       {
+        if (int rc = trace_select(2, st)) return rc;
         ProfScope prof("synth_f16_kernel", st);
         synth_f16_kernel<<<grid256, kThreads, smem_s, st>>>(g, g.B, g.N, n, b, t, sc, a->rgb, a->dbg_pre0);
         MOTIF_LAUNCHED("synth_f16_kernel");
