@@ -769,6 +769,317 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t 
 }
 
 // ======================================================================================================
+// Third-generation pipeline ("quad"): FOUR 128-row tiles in flight per SM, four epilogue warps each (thread == row,
+// all 64 columns), one issuer warp per tile.  The pipeline traces of the two-tile kernels (profiles/r1_trace_*) show
+// every tile spending most of its life waiting for a hand-off (MMA round trip, global-load or atomic latency) with
+// only one other tile to fill the SM; four independent chains keep the issue slots and the MUFU pipe busy.
+// Per tile 128 TMEM columns: [0,32) A_hi [32,64) A_lo [64,128) D.  A single accumulator suffices: the epilogue
+// copies all 64 columns into registers and releases D at once, so the next block's MMAs overlap its arithmetic.
+// ======================================================================================================
+constexpr int kQTileCols = 128;
+constexpr uint32_t kQColA = 0, kQColD = 64;
+
+struct QBars {
+  uint64_t w_full;
+  uint64_t a_ready[4];  // 128 arrivals: A operand published (implies D drained)
+  uint64_t d_ready[4];  // tcgen05.commit
+  uint64_t d_free[4];   // 128 arrivals: accumulator copied into registers
+  uint32_t tmem_base;
+};
+template <int NIMG>
+struct QSmem {
+  unsigned char img[NIMG][kBlkBytes];  // must stay first (1024-byte aligned swizzle atoms)
+  float consts[2048];
+  QBars bars;
+};
+struct QStep {
+  unsigned char img;   // weight block
+  unsigned char wait;  // 1: a_ready (new A operand), 2: d_free (same A, accumulator drained)
+};
+
+__device__ __forceinline__ uint32_t q_setup(QBars& bars) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.w_full, 1);
+    for (int t = 0; t < 4; ++t) {
+      mbar_init(&bars.a_ready[t], 128);
+      mbar_init(&bars.d_ready[t], 1);
+      mbar_init(&bars.d_free[t], 128);
+    }
+    fence_mbar_init();
+  }
+#ifdef MOTIF_TRACE
+  if (threadIdx.x < 4) trace_counters()[threadIdx.x] = 0;
+#endif
+  if (warp == 2) tmem_alloc<512>(&bars.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (bars.tmem_base != 0) __trap();
+  return bars.tmem_base;
+}
+
+// number of work items of tile slot `tile` of this CTA: item(it) = 4 * (blockIdx.x + it * gridDim.x) + tile
+__device__ __forceinline__ int q_iters(int n_items, int tile) {
+  const int first = 4 * (int)blockIdx.x + tile, stride = 4 * (int)gridDim.x;
+  return first < n_items ? (n_items - first + stride - 1) / stride : 0;
+}
+
+template <int tile, int NSTEPS>
+__device__ __forceinline__ void q_issuer(QBars& bars, const unsigned char* img_base, const QStep (&prog)[NSTEPS], int n_iters) {
+  constexpr uint32_t idesc = idesc_f16(128, 64);
+  constexpr uint32_t acol = tile * kQTileCols + kQColA, dcol = tile * kQTileCols + kQColD;
+  uint32_t ph_a = 0, ph_f = 0;
+  const uint64_t img_desc = smem_desc_sw128(smem_u32(img_base));
+  mbar_wait(&bars.w_full, 0);
+  for (int it = 0; it < n_iters; ++it) {
+#pragma unroll 1
+    for (int s = 0; s < NSTEPS; ++s) {
+      const QStep st = prog[s];
+      const uint64_t bhi = img_desc + (uint64_t)(st.img * (kBlkBytes >> 4));
+      const uint64_t blo = bhi + (kBlkHalf >> 4);
+      if (st.wait == 1) {
+        mbar_wait(&bars.a_ready[tile], ph_a);
+        ph_a ^= 1;
+      } else {
+        mbar_wait(&bars.d_free[tile], ph_f);
+        ph_f ^= 1;
+      }
+      tc_fence_after();
+      TRACE(1000 + 100 * (tile & 1) + s);
+      if (elect_one()) {
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a = (term == 1) ? acol + 32 : acol;
+          const uint64_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) mma_f16_ts(dcol, a + ks * 8, b + 2 * ks, idesc, (term | ks) != 0);
+        }
+        mma_commit(&bars.d_ready[tile]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+struct QEpi {
+  QBars* bars;
+  int tile, quad;
+  uint32_t lane_addr;  // TMEM address of this thread's lane, column 0 of its tile
+  uint32_t ph_d;
+};
+__device__ __forceinline__ QEpi q_make_epi(QBars& bars) {
+  const int w = (threadIdx.x >> 5) - kEpiWarp0;
+  QEpi c;
+  c.bars = &bars;
+  c.tile = w >> 2;
+  c.quad = w & 3;
+  c.lane_addr = c.tile * kQTileCols + ((uint32_t)(c.quad * 32) << 16);
+  c.ph_d = 0;
+  return c;
+}
+#ifdef MOTIF_TRACE
+#define TRACE_Q(c, k) do { if ((c).quad == 0 && (c).tile < 2 && (threadIdx.x & 31) == 0) trace(2 + (c).tile, 100 * (c).tile + (k)); } while (0)
+#else
+#define TRACE_Q(c, k) do { } while (0)
+#endif
+// all 64 accumulator columns of this thread's row into registers
+__device__ __forceinline__ void q_take_d(QEpi& c, uint32_t (&r)[64], bool release) {
+  mbar_wait(&c.bars->d_ready[c.tile], c.ph_d);
+  c.ph_d ^= 1;
+  tc_fence_after();
+  TRACE_Q(c, 10);
+  tmem_ld64(c.lane_addr + kQColD, r);
+  if (release) {
+    tc_fence_before();
+    mbar_arrive(&c.bars->d_free[c.tile]);
+  }
+}
+__device__ __forceinline__ void q_publish(QEpi& c) {
+  tmem_wait_st();
+  tc_fence_before();
+  mbar_arrive(&c.bars->a_ready[c.tile]);
+  TRACE_Q(c, 20);
+}
+// First layer from the LR table: v = sin(P0'[row] + e.x + e.y * rel_y + e.z * rel_x) (everything pre-scaled by 30)
+__device__ __forceinline__ void q_table_layer0(QEpi& c, const float* __restrict__ p0row, const float4* __restrict__ e0, float rel_y, float rel_x) {
+  const float4* src = reinterpret_cast<const float4*>(p0row);
+  float4 p[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 16; ++j4) p[j4] = __ldg(src + j4);
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 pp = p[(c0 >> 2) + j4];
+      const float pv[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 e = e0[c0 + 4 * j4 + u];
+        v[4 * j4 + u] = __sinf(pv[u] + fmaf(e.z, rel_x, fmaf(e.y, rel_y, e.x)));
+      }
+    }
+    split_store16(c.lane_addr + kQColA + c0 / 2, v);
+  }
+  q_publish(c);
+}
+// 64 -> 64 sine layer: D -> sin(s * D + cb) -> A.   s = 30 / weight scale, cb = 30 * bias (smem)
+__device__ __forceinline__ void q_sine_epilogue(QEpi& c, float s, const float* __restrict__ cb) {
+  uint32_t r[64];
+  q_take_d(c, r, false);
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 b = *reinterpret_cast<const float4*>(cb + c0 + 4 * j4);
+      v[4 * j4 + 0] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 0]), s, b.x));
+      v[4 * j4 + 1] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 1]), s, b.y));
+      v[4 * j4 + 2] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 2]), s, b.z));
+      v[4 * j4 + 3] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 3]), s, b.w));
+    }
+    split_store16(c.lane_addr + kQColA + c0 / 2, v);
+  }
+  q_publish(c);
+}
+// 64 hidden units of a 64 -> 256 sine-layer chunk, followed by the 256 -> 3 linear layer on CUDA cores.
+// cw[j] = (30 * bias_j, w_out[0][j], w_out[1][j], w_out[2][j]) (smem, the chunk's 64 units)
+__device__ __forceinline__ void q_sine_out3(QEpi& c, float s, const float4* __restrict__ cw, bool release, float& o0, float& o1, float& o2) {
+  uint32_t r[64];
+  q_take_d(c, r, release);
+  float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const float4 w = cw[j];
+    const float v = __sinf(fmaf(__uint_as_float(r[j]), s, w.x));
+    p0[j & 3] = fmaf(v, w.y, p0[j & 3]);
+    p1[j & 3] = fmaf(v, w.z, p1[j & 3]);
+    p2[j & 3] = fmaf(v, w.w, p2[j & 3]);
+  }
+  o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
+  o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+  o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// flow_imnet + binning of the three forward splats, quad pipeline.  Work item = (reference frame, 128-pixel tile).
+// ------------------------------------------------------------------------------------------------------
+__constant__ QStep kQProgF[5] = {{0, 1}, {1, 1}, {2, 2}, {3, 2}, {4, 2}};
+using QSmemF = QSmem<5>;
+
+__global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g, int B, int N, int n, int b, float t, float alpha, Scratch sc,
+                                                                float* __restrict__ flow_out) {
+  extern __shared__ unsigned char smem_raw[];
+  QSmemF& sm = *reinterpret_cast<QSmemF*>(align1024(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW, P = g.H * g.W;
+  const int n_items = 2 * ((qs + 127) / 128);
+  const float* wp = sc.wpack;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * i);
+    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(fmaf(e.y, t, e.x) * kOmega, e.z * kOmega, e.w * kOmega, 0.f);
+    sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<float4*>(sm.consts + 320)[i] =
+        make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 512 + i]);
+  if (threadIdx.x < 3) sm.consts[1344 + threadIdx.x] = wp[WeightPack::f_b3 + threadIdx.x];
+  if (threadIdx.x < 2) sm.consts[1348 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScF1 + threadIdx.x];
+  q_setup(sm.bars);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.bars.w_full, 5u * kBlkBytes);
+      for (int i = 0; i < 5; ++i) bulk_g2s(&sm.img[i][0], sc.wimg + (size_t)(kImgF1 + i) * kBlkBytes, kBlkBytes, &sm.bars.w_full);
+    }
+    __syncwarp();
+    q_issuer<0>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 0));
+  } else if (warp == 1) {
+    q_issuer<1>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 1));
+  } else if (warp == 2) {
+    q_issuer<2>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 2));
+  } else if (warp == 3) {
+    q_issuer<3>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 3));
+  } else {
+    QEpi c = q_make_epi(sm.bars);
+    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
+    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
+    const float s1 = sm.consts[1348], s2 = sm.consts[1349];
+    const int row = c.quad * 32 + lane;
+    const int n_iters = q_iters(n_items, c.tile);
+    for (int it = 0; it < n_iters; ++it) {
+      TRACE_Q(c, 1);
+      const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
+      const int r = item & 1;
+      const int rb = r * B + b;
+      const int q = (item >> 1) * 128 + row;
+      const bool live = q < qs;
+      const int qc = live ? q : qs - 1;
+      const int qy = qc / g.WW, qx = qc % g.WW;
+      const Query qu = make_query(qy, qx, g);
+      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
+      q_table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
+      q_sine_epilogue(c, s1, sm.consts + 256);
+      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
+      TRACE_Q(c, 2);
+
+      // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
+      const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
+      const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
+      const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
+      const float e = expf(z);
+      if (live && flow_out != nullptr) {
+        float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
+        fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
+        fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
+      }
+      const Footprint f = footprint(qx, qy, fx, fy);
+      if (live && f.finite) {
+        const uint32_t id = (uint32_t)((size_t)rb * qs + q);
+        const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
+        int slot[4];
+        size_t dd[4];
+        bool ok[4];
+        // all four slot requests go out before any of them is consumed
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
+          ok[k] = !((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH));
+          dd[k] = (size_t)b * qs + (size_t)(ok[k] ? cy : 0) * g.WW + (ok[k] ? cx : 0);
+          slot[k] = ok[k] ? atomicAdd(sc.bin_count + dd[k], 1) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (!ok[k]) continue;
+          const size_t d = dd[k];
+          const float wk = f.w[k];
+          const float we = __fmul_rn(e, wk);
+          red_add_v4(sc.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
+          // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
+          if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
+          if (slot[k] < kSlots) {
+            sc.bin_ent[d * kSlots + slot[k]] = make_uint2(id, __float_as_uint(we));
+          } else {
+            const float4* y4 = reinterpret_cast<const float4*>(sc.Y + (size_t)id * 64);
+            float* sp = sc.spill + d * 64;
+#pragma unroll 4
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 y = __ldg(y4 + j4);
+              red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
+            }
+          }
+        }
+      }
+      TRACE_Q(c, 4);
+    }
+  }
+  teardown(0);
+}
+
+// ======================================================================================================
 // gather + blend + synth_net (per timestamp).  Tiles 0 / 1 are two consecutive 128-pixel destination tiles.
 // ======================================================================================================
 constexpr int kNumStepsS = 6;
@@ -1070,12 +1381,15 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   if (a->n_begin == a->n_end) return 0;
   MOTIF_REQUIRE(a->dbg_synth_in == nullptr, "decode: dbg_synth_in is only produced by precision fp32 / tf32x3 (f16x3 never forms the 198-channel input)");
   const size_t qs = (size_t)g.HH * g.WW;
+  const int smem_fq = (int)sizeof(QSmemF) + 1024;
+  static const bool old_flow = getenv("MOTIF_FLOW_OLD") != nullptr;
   const int smem_i = (int)sizeof(SmemI) + 1024, smem_f = (int)sizeof(SmemF) + 1024, smem_s = (int)sizeof(SmemS) + 1024;
   static bool attr_done = false;
   static int n_sm = 148;
   if (!attr_done) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
@@ -1102,7 +1416,12 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       {
         if (int rc = trace_select(1, st)) return rc;
         ProfScope prof("flow_bin_f16_kernel", st);
-        flow_bin_f16_kernel<<<grid128, kThreads, smem_f, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
+        if (old_flow) {
+          flow_bin_f16_kernel<<<grid128, kThreads, smem_f, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
+        } else {
+          const int groups = ceil_div(2LL * tiles128, 4);
+          flow_bin_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
+        }
         MOTIF_LAUNCHED("flow_bin_f16_kernel");
       }
       {
