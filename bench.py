@@ -232,7 +232,7 @@ def main():
     if rank == 0:
         sampler.start()
     kernel_names = ["imnet_kernel", "flow_splat_kernel", "synth_kernel", "imnet_tc_kernel", "flow_splat_tc_kernel", "synth_tc_kernel",
-                    "imnet_f16_kernel", "flow_bin_f16_kernel", "synth_f16_kernel"]
+                    "imnet_f16_kernel", "flow_bin_f16_kernel", "synth_f16_kernel", "gather_l0_kernel"]
     ms, launches = timed(False, args.steps, profile=True)
     prof = _lib.prof_collect(kernel_names)
     _lib.prof_enable(False)
@@ -260,6 +260,7 @@ def main():
         "flow_splat_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "flow_splat_tc_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs,
         "synth_kernel": FLOP_SYNTH_ROW * qs, "synth_tc_kernel": FLOP_SYNTH_ROW * qs,
         "imnet_f16_kernel": FLOP_IMNET_ROW * 2 * B * qs, "flow_bin_f16_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "synth_f16_kernel": FLOP_SYNTH_ROW * qs,
+        "gather_l0_kernel": 0,
     }
     live = {k: v for k, v in prof.items() if v[1] > 0}
     # tensor peak of the operand type the MMAs run in: kind::f16 = the measured bf16/fp16 dense figure,

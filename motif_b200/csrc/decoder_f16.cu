@@ -104,8 +104,10 @@ struct Scratch {
   int* bin_count;           // [B][qs]
   uint2* bin_ent;           // [B][qs][kSlots] (source id, e*w)
   float* spill;             // [B][qs][64]  contributions that found no list slot
+  uint32_t* a0;             // [B][blocks * 256][64] sin(synth_net layer-0 pre-activation): 32 fp16 hi pairs, 32 lo pairs
 };
 
+constexpr int kGWh = 32, kGHh = 8;  // destination block of the gather kernel (kGW x kGH below)
 static int layout(int B, int H, int W, int HH, int WW, Scratch* s, char* base, size_t* bytes) {
   const size_t qs = (size_t)HH * WW, P = (size_t)H * W;
   size_t off = 0;
@@ -129,6 +131,7 @@ static int layout(int B, int H, int W, int HH, int WW, Scratch* s, char* base, s
   t.bin_count = (int*)take(sizeof(int) * B * qs);
   t.bin_ent = (uint2*)take(sizeof(uint2) * B * qs * kSlots);
   t.spill = (float*)take(sizeof(float) * B * qs * 64);
+  t.a0 = (uint32_t*)take(sizeof(uint32_t) * 64 * B * (size_t)((WW + kGWh - 1) / kGWh) * ((HH + kGHh - 1) / kGHh) * (kGWh * kGHh));
   if (s) *s = t;
   if (bytes) *bytes = off;
   return 0;
@@ -1288,6 +1291,254 @@ __global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, 
   teardown(tmem_base);
 }
 
+// ======================================================================================================
+// Destination gather of the three forward splats + blend + synth_net layer 0 (per timestamp), SIMT.
+// Split from the tensor-core kernel: the gather is a memory-latency problem (8 source rows of 256 B per destination on
+// average, two reference frames x four corners) that wants many warps and the whole L1, the MLP is an issue-slot
+// problem that wants the registers.  One CTA = a 32 x 8 block of destinations so that the source rows shared by
+// neighbouring destinations (each row is used by ~4 of them) are still in L1 when the neighbour asks; one warp = one
+// image row of the block, one destination at a time with the next one's rows in flight: half-warp <-> list entry
+// parity, lane <-> 4 channels (LDG.128).  Output: sin(layer-0 pre-activation) as fp16 hi/lo pairs, 256 B per
+// destination, in block order ("a-order", a0_position) -- the A operand of synth_net layer 1.
+// ======================================================================================================
+constexpr int kGW = 32, kGH = 8;  // destination block of one gather CTA
+
+// a-order -> pixel: a = ((block * 8 + row_in_block) * 32 + x_in_block)
+__device__ __forceinline__ bool a0_position(int a, int blocks_x, int HH, int WW, int& qy, int& qx) {
+  const int run = a >> 5, blk = run >> 3;
+  qy = (blk / blocks_x) * kGH + (run & 7);
+  qx = (blk % blocks_x) * kGW + (a & 31);
+  return (qy < HH) & (qx < WW);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool pred) {
+  const int sz = pred ? 16 : 0;  // src-size 0: the destination is zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 2) gather_l0_kernel(motif_geom_t g, int B, int N, int n, int b, float t, Scratch sc,
+                                                          float* __restrict__ dbg_pre0) {
+  __shared__ uint2 ent_s[kGH][kGW][kSlots];  // the warp's 32 destination lists (4 KB per warp)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
+  const int qs = g.HH * g.WW, P = g.H * g.W;
+  const int blocks_x = (g.WW + kGW - 1) / kGW;
+  const int qy = ((int)blockIdx.x / blocks_x) * kGH + warp;
+  const int x0 = ((int)blockIdx.x % blocks_x) * kGW;
+  if (qy >= g.HH) return;  // whole warps only; no block-wide barrier below
+  const int n_dest = min(kGW, g.WW - x0);
+  const size_t d0 = (size_t)b * qs + (size_t)qy * g.WW + x0;  // first destination of the warp
+  // ---- the 32 lists of the warp are contiguous (4 KB): asynchronous copy into shared memory ----
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(sc.bin_ent + d0 * kSlots);
+    uint4* dst = reinterpret_cast<uint4*>(&ent_s[warp][0][0]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = i * 32 + lane;  // 16-byte chunk; 8 chunks per destination
+      const bool on = (idx >> 3) < n_dest;
+      cp_async16(dst + idx, on ? src + idx : src, on);
+    }
+  }
+  // rank-1 input weights of this lane's two channels (4 l16 + 2 h, + 1), pre-scaled by 30:
+  // s_e0[ch] = (bias [in rtab], w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t, 0)
+  const int ch0 = 4 * l16 + 2 * h;
+  float rk[2][5], ct[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float* e = sc.wpack + WeightPack::s_e0 + 8 * (ch0 + u);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rk[u][i] = e[1 + i] * kOmega;
+    ct[u] = e[6] * t * kOmega;
+  }
+  // ---- per-destination scalars (Ours.py:813-814, 826-829, 834), lane <-> destination; re-arm the accumulators ----
+  float4 pa;        // 1/wz, dx', dy', zmax
+  float2 pb;        // count/16, wz/count
+  int cnt_l, lr_l;  // list length (-1: outside the image), nearest LR latent
+  {
+    const bool live = lane < n_dest;
+    const size_t d = d0 + (live ? lane : 0);
+    float4 side = make_float4(0.f, 0.f, 0.f, 0.f);
+    float zm = 1.0f;
+    int cnt_i = 0;
+    if (live) {
+      float4* side_p = reinterpret_cast<float4*>(sc.side + d * 4);
+      side = *side_p;
+      zm = sc.zmax[d];
+      cnt_i = sc.bin_count[d];
+      *side_p = make_float4(0.f, 0.f, 0.f, 0.f);
+      sc.zmax[d] = 1.0f;
+      sc.bin_count[d] = 0;
+    }
+    const float wz = side.z == 0.0f ? 1.0f : side.z;
+    const float cnt = (float)cnt_i;
+    const float cnt_ = cnt == 0.0f ? 1.0f : cnt;
+    const float wz_ = wz == 1.0f ? 0.0f : wz;
+    const float inv_wz = __fdiv_rn(1.0f, wz);
+    const Query qu = make_query(qy, min(x0 + lane, g.WW - 1), g);
+    pa = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
+    pb = make_float2(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_));
+    cnt_l = live ? cnt_i : -1;
+    lr_l = qu.iy * g.W + qu.ix;
+  }
+  cp_async_wait_all();
+  __syncwarp();
+
+  const float4* Y4 = reinterpret_cast<const float4*>(sc.Y);
+  const float2* R2 = reinterpret_cast<const float2*>(sc.rtab + (size_t)b * P * 64);
+  const int bn = b * N + n;
+  uint32_t* a0_out = sc.a0 + ((size_t)b * gridDim.x * (kGW * kGH) + ((size_t)blockIdx.x * kGH + warp) * kGW) * 64;
+
+  // rows of destination j: entry 2 i + h for this half-warp, i = 0..7 (predicated on the list length)
+  auto issue = [&](int j, float4 (&y)[8], float2& rr) {
+    const int cnt = min(__shfl_sync(0xffffffffu, cnt_l, j), kSlots);
+    const int lr = __shfl_sync(0xffffffffu, lr_l, j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t id = ent_s[warp][j][2 * i + h].x;
+      y[i] = (2 * i + h < cnt) ? __ldg(Y4 + (size_t)id * 16 + l16) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    rr = __ldg(R2 + ((size_t)lr * 64 + ch0) / 2);
+  };
+  auto finish = [&](int j, const float4 (&y)[8], const float2 rr) {
+    const int cnt_i = __shfl_sync(0xffffffffu, cnt_l, j);
+    const int cnt = min(cnt_i, kSlots);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float we = (2 * i + h < cnt) ? __uint_as_float(ent_s[warp][j][2 * i + h].y) : 0.0f;
+      acc.x = fmaf(we, y[i].x, acc.x);
+      acc.y = fmaf(we, y[i].y, acc.y);
+      acc.z = fmaf(we, y[i].z, acc.z);
+      acc.w = fmaf(we, y[i].w, acc.w);
+    }
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    const size_t d = d0 + j;
+    if (cnt_i > kSlots) {  // spilled contributions of an overfull list (warp-uniform branch)
+      float4* sp = reinterpret_cast<float4*>(sc.spill + d * 64) + l16;
+      const float4 v = *sp;
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      __syncwarp();
+      if (h == 0) *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float inv_wz = __shfl_sync(0xffffffffu, pa.x, j), dxp = __shfl_sync(0xffffffffu, pa.y, j), dyp = __shfl_sync(0xffffffffu, pa.z, j);
+    const float zm = __shfl_sync(0xffffffffu, pa.w, j), c16 = __shfl_sync(0xffffffffu, pb.x, j), wzc = __shfl_sync(0xffffffffu, pb.y, j);
+    float pre[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float lin = fmaf(rk[u][0], dxp, fmaf(rk[u][1], dyp, fmaf(rk[u][2], zm, fmaf(rk[u][3], c16, fmaf(rk[u][4], wzc, ct[u])))));
+      const float a = u == 0 ? (h ? acc.z : acc.x) : (h ? acc.w : acc.y);
+      pre[u] = fmaf(a, inv_wz, (u == 0 ? rr.x : rr.y) + lin);
+    }
+    if (cnt_i < 0) return;  // outside the image (warp-uniform)
+    if (dbg_pre0 != nullptr) {
+      const size_t dq = (size_t)qy * g.WW + x0 + j;
+      dbg_pre0[((size_t)bn * 64 + ch0) * qs + dq] = pre[0] * (1.0f / kOmega);
+      dbg_pre0[((size_t)bn * 64 + ch0 + 1) * qs + dq] = pre[1] * (1.0f / kOmega);
+    }
+    uint32_t hi, lo;
+    split_pair(__sinf(pre[0]), __sinf(pre[1]), hi, lo);
+    uint32_t* o = a0_out + (size_t)j * 64 + 2 * l16 + h;
+    o[0] = hi;
+    o[32] = lo;
+  };
+
+  float4 ya[8], yb[8];
+  float2 ra, rb2;
+  issue(0, ya, ra);
+#pragma unroll 1
+  for (int j = 0; j < kGW; j += 2) {
+    issue(j + 1, yb, rb2);
+    finish(j, ya, ra);
+    if (j + 2 < kGW) issue(j + 2, ya, ra);
+    finish(j + 1, yb, rb2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// synth_net layers 1..4 + clamp, quad pipeline.  Work item = 128 consecutive destinations in a-order.
+// ------------------------------------------------------------------------------------------------------
+__constant__ QStep kQProgS[6] = {{0, 1}, {1, 1}, {2, 1}, {3, 2}, {4, 2}, {5, 2}};
+using QSmemS = QSmem<6>;
+
+// consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) float4 per hidden unit (30 b3, w4[0], w4[1], w4[2])  [1152,1155) b4
+//         [1156] s1  [1157] s2  [1158] s3
+__global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, int B, int N, int n, int b, int n_items, Scratch sc, float* __restrict__ rgb) {
+  extern __shared__ unsigned char smem_raw[];
+  QSmemS& sm = *reinterpret_cast<QSmemS*>(align1024(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = g.HH * g.WW;
+  const int blocks_x = (g.WW + kGW - 1) / kGW;
+  const float* wp = sc.wpack;
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    sm.consts[i] = wp[WeightPack::s_b1 + i] * kOmega;
+    sm.consts[64 + i] = wp[WeightPack::s_b2 + i] * kOmega;
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    reinterpret_cast<float4*>(sm.consts + 128)[i] =
+        make_float4(wp[WeightPack::s_b3 + i] * kOmega, wp[WeightPack::s_a4 + i], wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 512 + i]);
+  if (threadIdx.x < 3) {
+    sm.consts[1152 + threadIdx.x] = wp[WeightPack::s_b4 + threadIdx.x];
+    sm.consts[1156 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScS1 + threadIdx.x];
+  }
+  q_setup(sm.bars);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&sm.bars.w_full, 6u * kBlkBytes);
+      for (int i = 0; i < 6; ++i) bulk_g2s(&sm.img[i][0], sc.wimg + (size_t)(kImgS1 + i) * kBlkBytes, kBlkBytes, &sm.bars.w_full);
+    }
+    __syncwarp();
+    q_issuer<0>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 0));
+  } else if (warp == 1) {
+    q_issuer<1>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 1));
+  } else if (warp == 2) {
+    q_issuer<2>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 2));
+  } else if (warp == 3) {
+    q_issuer<3>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 3));
+  } else {
+    QEpi c = q_make_epi(sm.bars);
+    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
+    const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
+    const int n_iters = q_iters(n_items, c.tile);
+    const uint4* a0 = reinterpret_cast<const uint4*>(sc.a0 + (size_t)b * n_items * 128 * 64);
+    for (int it = 0; it < n_iters; ++it) {
+      TRACE_Q(c, 1);
+      const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
+      const int a = item * 128 + c.quad * 32 + lane;
+      // layer-1 A operand: this row's 64 fp16 hi/lo pairs from the gather kernel
+      {
+        const uint4* src = a0 + (size_t)a * 16;
+        uint4 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = __ldg(src + k);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t w8[8] = {v[2 * k].x, v[2 * k].y, v[2 * k].z, v[2 * k].w, v[2 * k + 1].x, v[2 * k + 1].y, v[2 * k + 1].z, v[2 * k + 1].w};
+          tmem_st8(c.lane_addr + kQColA + 8 * k, w8);  // k < 4: hi columns [0,32), k >= 4: lo columns [32,64)
+        }
+        q_publish(c);
+      }
+      q_sine_epilogue(c, s1, sm.consts);
+      q_sine_epilogue(c, s2, sm.consts + 64);
+      float o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s3, cw + 64 * ch, ch < 3, o0, o1, o2);
+      TRACE_Q(c, 2);
+      int qy, qx;
+      if (a0_position(a, blocks_x, g.HH, g.WW, qy, qx)) {
+        float* out = rgb + ((size_t)(n * B + b) * 3) * qs + (size_t)qy * g.WW + qx;
+        out[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
+        out[(size_t)qs] = fminf(fmaxf(o1, 0.0f), 1.0f);
+        out[(size_t)2 * qs] = fminf(fmaxf(o2, 0.0f), 1.0f);
+      }
+    }
+  }
+  teardown(0);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
@@ -1383,6 +1634,9 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   const size_t qs = (size_t)g.HH * g.WW;
   const int smem_fq = (int)sizeof(QSmemF) + 1024;
   static const bool old_flow = getenv("MOTIF_FLOW_OLD") != nullptr;
+  static const bool old_synth = getenv("MOTIF_SYNTH_OLD") != nullptr;
+  const int smem_sq = (int)sizeof(QSmemS) + 1024;
+  const int g_blocks = ceil_div(g.WW, kGW) * ceil_div(g.HH, kGH);
   const int smem_i = (int)sizeof(SmemI) + 1024, smem_f = (int)sizeof(SmemF) + 1024, smem_s = (int)sizeof(SmemS) + 1024;
   static bool attr_done = false;
   static int n_sm = 148;
@@ -1390,6 +1644,8 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
+    MOTIF_CUDA(cudaFuncSetAttribute(synth_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sq));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 32));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
@@ -1424,10 +1680,21 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
         }
         MOTIF_LAUNCHED("flow_bin_f16_kernel");
       }
-      {
+      if (old_synth) {
         if (int rc = trace_select(2, st)) return rc;
         ProfScope prof("synth_f16_kernel", st);
         synth_f16_kernel<<<grid256, kThreads, smem_s, st>>>(g, g.B, g.N, n, b, t, sc, a->rgb, a->dbg_pre0);
+        MOTIF_LAUNCHED("synth_f16_kernel");
+      } else {
+        {
+          ProfScope prof("gather_l0_kernel", st);
+          gather_l0_kernel<<<g_blocks, 256, 0, st>>>(g, g.B, g.N, n, b, t, sc, a->dbg_pre0);
+          MOTIF_LAUNCHED("gather_l0_kernel");
+        }
+        if (int rc = trace_select(2, st)) return rc;
+        ProfScope prof("synth_f16_kernel", st);
+        const int items = 2 * g_blocks, groups = ceil_div(items, 4);
+        synth_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_sq, st>>>(g, g.B, g.N, n, b, items, sc, a->rgb);
         MOTIF_LAUNCHED("synth_f16_kernel");
       }
     }
