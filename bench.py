@@ -49,6 +49,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def load_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed
+    `ncu --set full` capture of this workload (profiles/r1_traffic.json; written by tools/ncu_traffic.py)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("traffic_bytes_per_launch", {})
+    return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -255,34 +265,47 @@ def main():
     d2h = N * B * 3 * qs * 4
 
     # ---- roofline of the dominant kernel of the step (per launch, CUDA events on the launch stream) ----
-    flops_per_launch = {
-        "imnet_kernel": FLOP_IMNET_ROW * 2 * B * qs, "imnet_tc_kernel": FLOP_IMNET_ROW * 2 * B * qs,
-        "flow_splat_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "flow_splat_tc_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs,
-        "synth_kernel": FLOP_SYNTH_ROW * qs, "synth_tc_kernel": FLOP_SYNTH_ROW * qs,
-        "imnet_f16_kernel": FLOP_IMNET_ROW * 2 * B * qs, "flow_bin_f16_kernel": FLOP_FLOW_IMNET_ROW * 2 * qs, "synth_f16_kernel": FLOP_SYNTH_ROW * qs,
-        "gather_l0_kernel": 0,
+    # Algorithmic work per launch.  Tensor-bound kernels: dense MACs of the reference's layers
+    # counted ONCE (the three split-product passes are not extra algorithmic FLOPs, so an error-compensated path
+    # cannot exceed 1/3 of the peak by construction).  HBM-bound kernel (gather_l0): bytes every destination pixel
+    # must move once -- 2 source rows (one per reference frame, 256 B each), its list entries (8 x 8 B on average),
+    # side/zmax/count read + re-arm (48 B), the 256-byte fp16 hi/lo A operand written for synth_net.
+    GATHER_BYTES_PER_DST = 2 * 256 + 64 + 48 + 256
+    work = {
+        "imnet_kernel": ("tensor", FLOP_IMNET_ROW * 2 * B * qs), "imnet_tc_kernel": ("tensor", FLOP_IMNET_ROW * 2 * B * qs),
+        "flow_splat_kernel": ("tensor", FLOP_FLOW_IMNET_ROW * 2 * qs), "flow_splat_tc_kernel": ("tensor", FLOP_FLOW_IMNET_ROW * 2 * qs),
+        "synth_kernel": ("tensor", FLOP_SYNTH_ROW * qs), "synth_tc_kernel": ("tensor", FLOP_SYNTH_ROW * qs),
+        "imnet_f16_kernel": ("tensor", FLOP_IMNET_ROW * 2 * B * qs), "flow_bin_f16_kernel": ("tensor", FLOP_FLOW_IMNET_ROW * 2 * qs),
+        "synth_f16_kernel": ("tensor", FLOP_SYNTH_ROW * qs), "gather_l0_kernel": ("hbm", GATHER_BYTES_PER_DST * qs),
     }
     live = {k: v for k, v in prof.items() if v[1] > 0}
-    # tensor peak of the operand type the MMAs run in: kind::f16 = the measured bf16/fp16 dense figure,
-    # kind::tf32 = half of it.  Algorithmic FLOPs count every MAC of the reference ONCE: the three split-product
-    # passes are not counted, so an error-compensated path cannot exceed 1/3 of this peak by construction.
+    # tensor peak of the operand type the MMAs run in: kind::f16 = the measured bf16/fp16 dense figure, kind::tf32 = half of it
     if args.precision == "f16x3":
         tensor_peak, peak_name = peaks["bf16_sustained"], "fp16 dense = bf16 sustained"
     else:
         tensor_peak, peak_name = peaks["bf16_sustained"] / 2.0, "TF32 dense = 0.5 x bf16 sustained"
+    traffic = load_traffic()
     kernels = {}
     for k, (tot_ms, cnt) in live.items():
         avg = tot_ms / cnt
-        kernels[k] = {"launches_per_step": cnt / args.steps, "avg_ms": avg, "share_of_step": tot_ms / ms,
-                      "tflops": flops_per_launch[k] / (avg * 1e-3) / 1e12}
+        bound, amount = work[k]
+        rate = amount / (avg * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+        peak = tensor_peak if bound == "tensor" else peaks["hbm_gbs"]
+        kernels[k] = {"launches_per_step": cnt / args.steps, "avg_ms": avg, "share_of_step": tot_ms / ms, "bound": bound,
+                      "achieved": rate, "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": rate / peak,
+                      "traffic": traffic.get(k)}
     roofline = None
     if live:
         dom = max(live, key=lambda k: live[k][0])
-        a = kernels[dom]["tflops"]
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": a, "peak": tensor_peak, "unit": "TFLOP/s", "frac": a / tensor_peak, "traffic": None,
-                    "peak_note": f"{peak_name}, {peaks['source']}; algorithmic FLOPs (K un-padded, one pass counted; 3 split-product passes run)"}
+        kd = kernels[dom]
+        peak = tensor_peak if kd["bound"] == "tensor" else peaks["hbm_gbs"]
+        note = (f"{peak_name}, {peaks['source']}; algorithmic FLOPs (K un-padded, one pass counted; 3 split-product passes run)" if kd["bound"] == "tensor"
+                else f"HBM copy bandwidth, {peaks['source']}; {GATHER_BYTES_PER_DST} algorithmic bytes per destination pixel")
+        roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": peak, "unit": kd["unit"], "frac": kd["frac"],
+                    "traffic": kd["traffic"], "peak_note": note}
         step_flops = (2 * FLOP_FLOW_IMNET_ROW + FLOP_SYNTH_ROW) * N * qs + FLOP_IMNET_ROW * 2 * B * qs
         roofline["whole_step_tflops"] = step_flops * args.steps / (ms * 1e-3) / 1e12
+        roofline["whole_step_tensor_frac"] = roofline["whole_step_tflops"] / tensor_peak
 
     # ---- HBM roofline of the stand-alone softmax splat operator (C=130, one 720x1280 reference frame) ----
     torch.manual_seed(0)
@@ -307,7 +330,7 @@ def main():
     gather_ms = sp["splat_gather_kernel"][0] / max(sp["splat_gather_kernel"][1], 1)
     alg_bytes = SPLAT_BYTES_PER_SRC * qs
     roofline_splat = {"kernel": "splat_gather_kernel", "bound": "hbm", "achieved": alg_bytes / (gather_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                      "frac": alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                      "frac": alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("splat_gather_kernel"),
                       "operator_gbs": alg_bytes / (op_ms * 1e-3) / 1e9, "operator_ms": op_ms,
                       "bin_ms": sp["splat_bin_kernel"][0] / max(sp["splat_bin_kernel"][1], 1),
                       "note": f"FunctionSoftsplat softmax, [1,130,{HH},{WW}], 1056 B per source pixel; {peaks['source']}"}
