@@ -286,9 +286,12 @@ def main():
         tensor_peak, peak_name = peaks["bf16_sustained"] / 2.0, "TF32 dense = 0.5 x bf16 sustained"
     traffic = load_traffic()
     kernels = {}
+    per_clip = ("imnet_kernel", "imnet_tc_kernel", "imnet_f16_kernel")
     for k, (tot_ms, cnt) in live.items():
         avg = tot_ms / cnt
         bound, amount = work[k]
+        if k not in per_clip:  # `work` is per timestamp; a launch covers a group of timestamps (f16x3: all of this rank's)
+            amount = amount * (n1 - n0) * args.steps / cnt
         rate = amount / (avg * 1e-3) / (1e12 if bound == "tensor" else 1e9)
         peak = tensor_peak if bound == "tensor" else peaks["hbm_gbs"]
         kernels[k] = {"launches_per_step": cnt / args.steps, "avg_ms": avg, "share_of_step": tot_ms / ms, "bound": bound,

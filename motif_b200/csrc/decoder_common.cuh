@@ -99,7 +99,7 @@ int decode_layout(int B, int N, int H, int W, int HH, int WW, DecodeScratch* s, 
 int decode_simt(const motif_decode_t* a, cudaStream_t st);
 int decode_tc(const motif_decode_t* a, cudaStream_t st);
 int decode_f16(const motif_decode_t* a, cudaStream_t st);
-size_t decode_f16_workspace_bytes(int B, int H, int W, int HH, int WW);
+size_t decode_f16_workspace_bytes(int B, int N, int H, int W, int HH, int WW);
 int check_decode(const motif_decode_t* a);
 size_t tc_image_bytes();
 int tc_set_trace(long long* buf, int capacity);

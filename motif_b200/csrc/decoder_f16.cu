@@ -89,7 +89,22 @@ static int trace_select(int kernel, cudaStream_t st) {
 enum { kImgF1 = 0, kImgF2 = 1, kImgI1 = 5, kImgI2 = 6, kImgI3 = 10, kImgS1 = 14, kImgS2 = 15, kImgS3 = 16, kNumImg = 20 };
 enum { kScF1 = 0, kScF2, kScI1, kScI2, kScI3, kScS1, kScS2, kScS3, kNumSc };
 
+constexpr int kMaxGroup = 8;  // timestamps decoded together (their lists, accumulators and A operands are all live)
+struct Times {
+  float t[kMaxGroup];
+};
+// by-value kernel parameter: select without a dynamically indexed (local-memory) copy
+__device__ __forceinline__ float time_of(const Times& ts, int i) {
+  float t = ts.t[0];
+#pragma unroll
+  for (int k = 1; k < kMaxGroup; ++k) t = (i == k) ? ts.t[k] : t;
+  return t;
+}
+
+// Per-timestamp arrays carry a leading [NT] dimension (NT = timestamps per group): element (nl, b, q) of an array
+// with k values per pixel lives at ((nl * B + b) * qs + q) * k.
 struct Scratch {
+  uint32_t* armed;          // [4] magic words: set while side / bin_count / spill are all-zero and zmax all-one
   float* wpack;             // WeightPack (fp32, checkpoint values regrouped)
   float* fold;              // [64][256] W0a*W3 then [64] W0a*b3
   float* scales;            // [kNumSc] power-of-two weight scales, then [kNumSc] their inverses
@@ -99,16 +114,17 @@ struct Scratch {
   float* ftab;              // [2B][P][64]  30 * W0b * feat
   float* rtab;              // [B][P][64]   30 * (W0c * residual + b0)
   float* Y;                 // [2B][qs][64] 30 * (W0a*imnet(q) + W0b*feat[nearest(q)]) per source pixel
-  float* side;              // [B][qs][4]   sum e*dx*w, sum e*dy*w, sum e*w, count
-  float* zmax;              // [B][qs]      max splat of e, starts at 1
-  int* bin_count;           // [B][qs]
-  uint2* bin_ent;           // [B][qs][kSlots] (source id, e*w)
-  float* spill;             // [B][qs][64]  contributions that found no list slot
-  uint32_t* a0;             // [B][blocks * 256][64] sin(synth_net layer-0 pre-activation): 32 fp16 hi pairs, 32 lo pairs
+  float* side;              // [NT][B][qs][4]   sum e*dx*w, sum e*dy*w, sum e*w, count
+  int* bin_count;           // [NT][B][qs]
+  float* spill;             // [NT][B][qs][64]  contributions that found no list slot
+  float* zmax;              // [NT][B][qs]      max splat of e, starts at 1
+  uint2* bin_ent;           // [NT][B][qs][kSlots] (source id, e*w)
+  uint32_t* a0;             // [NT][B][blocks * 256][64] sin(synth_net layer-0 pre-activation): 32 fp16 hi pairs, 32 lo pairs
+  size_t zero_bytes;        // side | bin_count | spill are contiguous: the region the arming pass clears
 };
 
 constexpr int kGWh = 32, kGHh = 8;  // destination block of the gather kernel (kGW x kGH below)
-static int layout(int B, int H, int W, int HH, int WW, Scratch* s, char* base, size_t* bytes) {
+static int layout(int B, int NT, int H, int W, int HH, int WW, Scratch* s, char* base, size_t* bytes) {
   const size_t qs = (size_t)HH * WW, P = (size_t)H * W;
   size_t off = 0;
   auto take = [&](size_t nbytes) {
@@ -117,6 +133,7 @@ static int layout(int B, int H, int W, int HH, int WW, Scratch* s, char* base, s
     return p;
   };
   Scratch t;
+  t.armed = (uint32_t*)take(16);
   t.wpack = (float*)take(sizeof(float) * WeightPack::total);
   t.fold = (float*)take(sizeof(float) * (64 * 256 + 64));
   t.scales = (float*)take(sizeof(float) * 2 * kNumSc);
@@ -126,12 +143,14 @@ static int layout(int B, int H, int W, int HH, int WW, Scratch* s, char* base, s
   t.ftab = (float*)take(sizeof(float) * 2 * B * P * 64);
   t.rtab = (float*)take(sizeof(float) * B * P * 64);
   t.Y = (float*)take(sizeof(float) * 2 * B * qs * 64);
-  t.side = (float*)take(sizeof(float) * B * qs * 4);
-  t.zmax = (float*)take(sizeof(float) * B * qs);
-  t.bin_count = (int*)take(sizeof(int) * B * qs);
-  t.bin_ent = (uint2*)take(sizeof(uint2) * B * qs * kSlots);
-  t.spill = (float*)take(sizeof(float) * B * qs * 64);
-  t.a0 = (uint32_t*)take(sizeof(uint32_t) * 64 * B * (size_t)((WW + kGWh - 1) / kGWh) * ((HH + kGHh - 1) / kGHh) * (kGWh * kGHh));
+  const size_t z0 = off;
+  t.side = (float*)take(sizeof(float) * NT * B * qs * 4);
+  t.bin_count = (int*)take(sizeof(int) * NT * B * qs);
+  t.spill = (float*)take(sizeof(float) * NT * B * qs * 64);
+  t.zero_bytes = off - z0;
+  t.zmax = (float*)take(sizeof(float) * NT * B * qs);
+  t.bin_ent = (uint2*)take(sizeof(uint2) * NT * B * qs * kSlots);
+  t.a0 = (uint32_t*)take(sizeof(uint32_t) * 64 * NT * B * (size_t)((WW + kGWh - 1) / kGWh) * ((HH + kGHh - 1) / kGHh) * (kGWh * kGHh));
   if (s) *s = t;
   if (bytes) *bytes = off;
   return 0;
@@ -257,8 +276,22 @@ __global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float
   }
 }
 
-__global__ void fill_kernel(float* p, float v, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+// Arming of the per-destination accumulators.  The consumer (gather_l0_kernel) re-arms every cell it reads, so
+// between two complete decodes side / bin_count / spill are all-zero and zmax all-one: the 1.7 GB clear of a
+// 7-timestamp Adobe group is paid once per workspace, not once per clip.  `armed` holds four magic words while the
+// invariant holds for this geometry; decode clears them right after this pass and sets them again at its very end,
+// so an aborted decode or a workspace used by anything else is cleared on the next call.
+struct Magic {
+  uint32_t w[4];
+};
+__global__ void arm_kernel(const uint32_t* __restrict__ armed, Magic m, uint4* __restrict__ zero_base, size_t n16, float* __restrict__ zmax, size_t nz) {
+  if (armed[0] == m.w[0] && armed[1] == m.w[1] && armed[2] == m.w[2] && armed[3] == m.w[3]) return;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = i0; i < n16; i += stride) zero_base[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = i0; i < nz; i += stride) zmax[i] = 1.0f;
+}
+__global__ void mark_kernel(uint32_t* armed, Magic m) {
+  if (threadIdx.x < 4) armed[threadIdx.x] = m.w[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -657,121 +690,6 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 }
 
 // ======================================================================================================
-// flow_imnet + binning of the three forward splats (per timestamp).  Tile 0 / 1 = reference frame 0 / 1.
-// ======================================================================================================
-constexpr int kNumStepsF = 5;
-__constant__ Step kProgF[kNumStepsF] = {
-    {0, 0, 0, 1, 0, 1, 0},  // layer 1
-    {1, 0, 0, 1, 0, 1, 0},  // layer 2 units 0..63    -> D0
-    {2, 1, 0, 0, 0, 1, 0},  //         units 64..127  -> D1
-    {3, 0, 0, 0, 0, 1, 0},  //         units 128..191 -> D0
-    {4, 1, 0, 0, 0, 1, 0},  //         units 192..255 -> D1
-};
-using SmemF = Smem<5, 0>;
-
-// consts: [0,256) e0 float4 (30 (b0 + w_t t), 30 w_rely, 30 w_relx, 0)  [256,320) 30 b1
-//         [320,1344) float4 per hidden unit (30 b2, w3[0], w3[1], w3[2])  [1344,1347) b3  [1348] s1 [1349] s2
-__global__ void __launch_bounds__(kThreads, 1) flow_bin_f16_kernel(motif_geom_t g, int B, int N, int n, int b, float t, float alpha, Scratch sc,
-                                                                  float* __restrict__ flow_out) {
-  extern __shared__ unsigned char smem_raw[];
-  SmemF& sm = *reinterpret_cast<SmemF*>(align1024(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int n_tiles = (qs + 127) / 128;
-  const int n_iters = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const float* wp = sc.wpack;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * i);
-    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(fmaf(e.y, t, e.x) * kOmega, e.z * kOmega, e.w * kOmega, 0.f);
-    sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
-  }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    reinterpret_cast<float4*>(sm.consts + 320)[i] =
-        make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 512 + i]);
-  if (threadIdx.x < 3) sm.consts[1344 + threadIdx.x] = wp[WeightPack::f_b3 + threadIdx.x];
-  if (threadIdx.x < 2) sm.consts[1348 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScF1 + threadIdx.x];
-  const uint32_t tmem_base = setup(sm.bars);
-
-  if (warp == 0) {
-    if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgF1, 5, sm.bars);
-  } else if (warp == 1) {
-    issuer_loop<0>(sm.bars, &sm.img[0][0], &sm.img[0][0], kProgF, n_iters);
-  } else if (warp == 3) {
-    issuer_loop<1>(sm.bars, &sm.img[0][0], &sm.img[0][0], kProgF, n_iters);
-  } else if (warp >= kEpiWarp0) {
-    Epi c = make_epi(sm.bars, tmem_base);
-    const int r = c.tile;
-    const int rb = r * B + b;
-    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
-    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
-    const float s1 = sm.consts[1348], s2 = sm.consts[1349];
-    const int row = c.quad * 32 + lane;
-    for (int it = 0; it < n_iters; ++it) {
-      TRACE_EPI(c, 1);
-      const int tile_id = blockIdx.x + it * gridDim.x;
-      const int q = tile_id * 128 + row;
-      const bool live = q < qs;
-      const int qc = live ? q : qs - 1;
-      const int qy = qc / g.WW, qx = qc % g.WW;
-      const Query qu = make_query(qy, qx, g);
-      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
-      table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
-      sine_epilogue(c, 0, s1, sm.consts + 256, kColA, &sm.bars.a_ready[c.tile], false);
-      float dx = 0.f, dy = 0.f, zraw = 0.f;
-      if (c.half == 0) dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s2, cw + 64 * ch, dx, dy, zraw);
-      TRACE_EPI(c, 2);
-      combine_halves(sm, c, row, dx, dy, zraw);
-      TRACE_EPI(c, 3);
-
-      // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
-      const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
-      const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
-      const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
-      const float e = expf(z);
-      if (live && flow_out != nullptr && c.half == 0) {
-        float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
-        fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
-        fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
-      }
-      const Footprint f = footprint(qx, qy, fx, fy);
-      if (live && f.finite) {
-        const uint32_t id = (uint32_t)((size_t)rb * qs + q);
-        const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
-        // the two warps of a row take two corners each (half 0: north, half 1: south)
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const int k = 2 * c.half + kk;
-          const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
-          if ((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH)) continue;
-          const size_t d = (size_t)b * qs + (size_t)cy * g.WW + cx;
-          const float wk = kk == 0 ? (c.half ? f.w[2] : f.w[0]) : (c.half ? f.w[3] : f.w[1]);
-          const float we = __fmul_rn(e, wk);
-          const int slot = atomicAdd(sc.bin_count + d, 1);
-          if (slot < kSlots) {
-            sc.bin_ent[d * kSlots + slot] = make_uint2(id, __float_as_uint(we));
-          } else {
-            const float4* y4 = reinterpret_cast<const float4*>(sc.Y + (size_t)id * 64);
-            float* sp = sc.spill + d * 64;
-#pragma unroll 4
-            for (int j4 = 0; j4 < 16; ++j4) {
-              const float4 y = __ldg(y4 + j4);
-              red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
-            }
-          }
-          red_add_v4(sc.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
-          // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
-          if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
-        }
-      }
-      TRACE_EPI(c, 4);
-    }
-  }
-  teardown(tmem_base);
-}
-
-// ======================================================================================================
 // Third-generation pipeline ("quad"): FOUR 128-row tiles in flight per SM, four epilogue warps each (thread == row,
 // all 64 columns), one issuer warp per tile.  The pipeline traces of the two-tile kernels (profiles/r1_trace_*) show
 // every tile spending most of its life waiting for a hand-off (MMA round trip, global-load or atomic latency) with
@@ -792,7 +710,7 @@ struct QBars {
 template <int NIMG>
 struct QSmem {
   unsigned char img[NIMG][kBlkBytes];  // must stay first (1024-byte aligned swizzle atoms)
-  float consts[2048];
+  float consts[2048 + 256 * kMaxGroup];
   QBars bars;
 };
 struct QStep {
@@ -970,20 +888,23 @@ __device__ __forceinline__ void q_sine_out3(QEpi& c, float s, const float4* __re
 // ------------------------------------------------------------------------------------------------------
 __constant__ QStep kQProgF[5] = {{0, 1}, {1, 1}, {2, 2}, {3, 2}, {4, 2}};
 using QSmemF = QSmem<5>;
-
-__global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g, int B, int N, int n, int b, float t, float alpha, Scratch sc,
+// consts: [0,256) unused  [256,320) 30 b1  [320,1344) float4 per hidden unit (30 b2, w3[0], w3[1], w3[2])  [1344,1347) b3
+//         [1348] s1 [1349] s2   [2048 + 256 nl, +256) e0 of timestamp nl: float4 (30 (b0 + w_t t), 30 w_rely, 30 w_relx, 0)
+// Work item = (timestamp of the group, reference frame, 128-pixel tile), timestamp-major.
+__global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, float alpha, Scratch sc,
                                                                 float* __restrict__ flow_out) {
   extern __shared__ unsigned char smem_raw[];
   QSmemF& sm = *reinterpret_cast<QSmemF*>(align1024(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int n_items = 2 * ((qs + 127) / 128);
+  const int items_per_t = 2 * ((qs + 127) / 128);
+  const int n_items = nt * items_per_t;
   const float* wp = sc.wpack;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * i);
-    reinterpret_cast<float4*>(sm.consts)[i] = make_float4(fmaf(e.y, t, e.x) * kOmega, e.z * kOmega, e.w * kOmega, 0.f);
-    sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
+  for (int i = threadIdx.x; i < 64 * nt; i += blockDim.x) {
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * (i & 63));
+    reinterpret_cast<float4*>(sm.consts + 2048)[i] = make_float4(fmaf(e.y, time_of(times, i >> 6), e.x) * kOmega, e.z * kOmega, e.w * kOmega, 0.f);
   }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
   for (int i = threadIdx.x; i < 256; i += blockDim.x)
     reinterpret_cast<float4*>(sm.consts + 320)[i] =
         make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 512 + i]);
@@ -1006,7 +927,6 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
     q_issuer<3>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 3));
   } else {
     QEpi c = q_make_epi(sm.bars);
-    const float4* e0 = reinterpret_cast<const float4*>(sm.consts);
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
     const float s1 = sm.consts[1348], s2 = sm.consts[1349];
     const int row = c.quad * 32 + lane;
@@ -1014,9 +934,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
     for (int it = 0; it < n_iters; ++it) {
       TRACE_Q(c, 1);
       const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
-      const int r = item & 1;
+      const int nl = item / items_per_t, rem = item - nl * items_per_t;
+      const int n = n0 + nl;
+      const float4* e0 = reinterpret_cast<const float4*>(sm.consts + 2048 + 256 * nl);
+      const int r = rem & 1;
       const int rb = r * B + b;
-      const int q = (item >> 1) * 128 + row;
+      const int q = (rem >> 1) * 128 + row;
       const bool live = q < qs;
       const int qc = live ? q : qs - 1;
       const int qy = qc / g.WW, qx = qc % g.WW;
@@ -1042,6 +965,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       const Footprint f = footprint(qx, qy, fx, fy);
       if (live && f.finite) {
         const uint32_t id = (uint32_t)((size_t)rb * qs + q);
+        const size_t dbase = ((size_t)nl * B + b) * qs;  // this timestamp's destination arrays
         const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
         int slot[4];
         size_t dd[4];
@@ -1051,7 +975,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
         for (int k = 0; k < 4; ++k) {
           const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
           ok[k] = !((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH));
-          dd[k] = (size_t)b * qs + (size_t)(ok[k] ? cy : 0) * g.WW + (ok[k] ? cx : 0);
+          dd[k] = dbase + (size_t)(ok[k] ? cy : 0) * g.WW + (ok[k] ? cx : 0);
           slot[k] = ok[k] ? atomicAdd(sc.bin_count + dd[k], 1) : 0;
         }
 #pragma unroll
@@ -1083,215 +1007,6 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
 }
 
 // ======================================================================================================
-// gather + blend + synth_net (per timestamp).  Tiles 0 / 1 are two consecutive 128-pixel destination tiles.
-// ======================================================================================================
-constexpr int kNumStepsS = 6;
-__constant__ Step kProgS[kNumStepsS] = {
-    {0, 0, 2, 1, 0, 1, 0},  // layer 1, A = sin(layer-0 pre-activation) from the shared-memory tile
-    {1, 0, 0, 1, 0, 1, 0},  // layer 2
-    {2, 0, 0, 1, 0, 1, 0},  // layer 3 units 0..63    -> D0
-    {3, 1, 0, 0, 0, 1, 0},  //         units 64..127  -> D1
-    {4, 0, 0, 0, 0, 1, 0},
-    {5, 1, 0, 0, 0, 1, 0},
-};
-constexpr int kGatherDests = 16;  // destinations per epilogue warp
-struct WarpStage {
-  uint2 ent[kGatherDests][kSlots];  // list entries of the warp's destinations
-  float4 par[kGatherDests][2];      // (1/wz, dx', dy', zmax), (count/16, wz/count, lr index bits, count bits)
-};
-constexpr int kSynthExtra = 2 * 2 * kBlkBytes + 16 * (int)sizeof(WarpStage);  // two A tiles (hi+lo, 128 rows) + staging
-using SmemS = Smem<6, kSynthExtra>;
-
-// consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) float4 per hidden unit (30 b3, w4[0], w4[1], w4[2])  [1152,1155) b4
-//         [1156] s1  [1157] s2  [1158] s3
-__global__ void __launch_bounds__(kThreads, 1) synth_f16_kernel(motif_geom_t g, int B, int N, int n, int b, float t, Scratch sc, float* __restrict__ rgb,
-                                                               float* __restrict__ dbg_pre0) {
-  extern __shared__ unsigned char smem_raw[];
-  SmemS& sm = *reinterpret_cast<SmemS*>(align1024(smem_raw));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int n_units = (qs + 255) / 256;
-  const int n_iters = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const float* wp = sc.wpack;
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
-    sm.consts[i] = wp[WeightPack::s_b1 + i] * kOmega;
-    sm.consts[64 + i] = wp[WeightPack::s_b2 + i] * kOmega;
-  }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    reinterpret_cast<float4*>(sm.consts + 128)[i] =
-        make_float4(wp[WeightPack::s_b3 + i] * kOmega, wp[WeightPack::s_a4 + i], wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 512 + i]);
-  if (threadIdx.x < 3) {
-    sm.consts[1152 + threadIdx.x] = wp[WeightPack::s_b4 + threadIdx.x];
-    sm.consts[1156 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScS1 + threadIdx.x];
-  }
-  const uint32_t tmem_base = setup(sm.bars);
-  unsigned char* a_tiles = sm.extra;  // 1024-aligned: follows the images
-
-  if (warp == 0) {
-    if (lane == 0) load_images(&sm.img[0][0], sc.wimg, kImgS1, 6, sm.bars);
-  } else if (warp == 1) {
-    issuer_loop<0>(sm.bars, &sm.img[0][0], a_tiles, kProgS, n_iters);
-  } else if (warp == 3) {
-    issuer_loop<1>(sm.bars, &sm.img[0][0], a_tiles + 2 * kBlkBytes, kProgS, n_iters);
-  } else if (warp >= kEpiWarp0) {
-    Epi c = make_epi(sm.bars, tmem_base);
-    WarpStage& ws = reinterpret_cast<WarpStage*>(sm.extra + 2 * 2 * kBlkBytes)[warp - kEpiWarp0];
-    unsigned char* a_hi = a_tiles + (size_t)c.tile * 2 * kBlkBytes;
-    unsigned char* a_lo = a_hi + 2 * kBlkHalf;
-    const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
-    const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
-    const int bn = b * N + n;
-    const int row = c.quad * 32 + lane;
-    // rank-1 input weights of this lane's two channels (2 lane, 2 lane + 1), pre-scaled by 30:
-    // s_e0[ch] = (bias [in rtab], w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t, 0)
-    float rk[2][5], ct[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float* e = wp + WeightPack::s_e0 + 8 * (2 * lane + u);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) rk[u][i] = e[1 + i] * kOmega;
-      ct[u] = e[6] * t * kOmega;
-    }
-    const float2* Y2 = reinterpret_cast<const float2*>(sc.Y);
-    const float2* R2 = reinterpret_cast<const float2*>(sc.rtab);
-
-    // issue the row loads of destination j (first 8 list entries + its residual-table row)
-    auto issue = [&](int j, float2 (&y)[8], float2& rr) {
-      const float4 pb = ws.par[j][1];
-      const int cnt = min(__float_as_int(pb.w), 8);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t id = ws.ent[j][k].x;
-        y[k] = k < cnt ? __ldg(Y2 + (size_t)id * 32 + lane) : make_float2(0.f, 0.f);
-      }
-      rr = __ldg(R2 + ((size_t)b * P + __float_as_int(pb.z)) * 32 + lane);
-    };
-    // blend, layer-0 pre-activation, sine, split, store into the shared-memory A tile
-    auto finish = [&](int j, int q_w, const float2 (&y)[8], const float2 rr) {
-      const float4 pa = ws.par[j][0], pb = ws.par[j][1];
-      const int cnt_i = __float_as_int(pb.w);
-      float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float we = k < cnt_i ? __uint_as_float(ws.ent[j][k].y) : 0.0f;
-        acc.x = fmaf(we, y[k].x, acc.x);
-        acc.y = fmaf(we, y[k].y, acc.y);
-      }
-      const int cnt = min(cnt_i, kSlots);
-      for (int k = 8; k < cnt; ++k) {  // long lists (rare)
-        const uint2 en = ws.ent[j][k];
-        const float2 v = __ldg(Y2 + (size_t)en.x * 32 + lane);
-        acc.x = fmaf(__uint_as_float(en.y), v.x, acc.x);
-        acc.y = fmaf(__uint_as_float(en.y), v.y, acc.y);
-      }
-      const int dq = q_w + j;
-      if (cnt_i > kSlots) {  // spilled contributions of an overfull list
-        float2* sp = reinterpret_cast<float2*>(sc.spill + ((size_t)b * qs + dq) * 64) + lane;
-        const float2 v = *sp;
-        acc.x += v.x;
-        acc.y += v.y;
-        *sp = make_float2(0.f, 0.f);
-      }
-      float pre[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float lin = fmaf(rk[u][0], pa.y, fmaf(rk[u][1], pa.z, fmaf(rk[u][2], pa.w, fmaf(rk[u][3], pb.x, fmaf(rk[u][4], pb.y, ct[u])))));
-        pre[u] = fmaf(u == 0 ? acc.x : acc.y, pa.x, (u == 0 ? rr.x : rr.y) + lin);
-      }
-      if (dbg_pre0 != nullptr && cnt_i >= 0) {
-        dbg_pre0[((size_t)bn * 64 + 2 * lane) * qs + dq] = pre[0] * (1.0f / kOmega);
-        dbg_pre0[((size_t)bn * 64 + 2 * lane + 1) * qs + dq] = pre[1] * (1.0f / kOmega);
-      }
-      uint32_t hi, lo;
-      split_pair(__sinf(pre[0]), __sinf(pre[1]), hi, lo);
-      const uint32_t off = sw128_offset_h(c.quad * 32 + c.half * kGatherDests + j, 2 * lane);
-      *reinterpret_cast<uint32_t*>(a_hi + off) = hi;
-      *reinterpret_cast<uint32_t*>(a_lo + off) = lo;
-    };
-
-    for (int it = 0; it < n_iters; ++it) {
-      TRACE_EPI(c, 1);
-      const int unit = blockIdx.x + it * gridDim.x;
-      const int q_t = unit * 256 + c.tile * 128;                       // first destination of the tile
-      const int q_w = q_t + c.quad * 32 + c.half * kGatherDests;       // first destination gathered by this warp
-      // ---- per-destination scalars (Ours.py:813-814, 826-829, 834), re-arm the accumulators ----
-      if (lane < kGatherDests) {
-        const int q = q_w + lane;
-        const bool live = q < qs;
-        const int qc = live ? q : qs - 1;
-        const size_t d = (size_t)b * qs + qc;
-        float4 side = make_float4(0.f, 0.f, 0.f, 0.f);
-        float zm = 1.0f;
-        int cnt_i = 0;
-        if (live) {
-          float4* side_p = reinterpret_cast<float4*>(sc.side + d * 4);
-          side = *side_p;
-          zm = sc.zmax[d];
-          cnt_i = sc.bin_count[d];
-          *side_p = make_float4(0.f, 0.f, 0.f, 0.f);
-          sc.zmax[d] = 1.0f;
-          sc.bin_count[d] = 0;
-        }
-        const float wz = side.z == 0.0f ? 1.0f : side.z;
-        const float cnt = (float)cnt_i;
-        const float cnt_ = cnt == 0.0f ? 1.0f : cnt;
-        const float wz_ = wz == 1.0f ? 0.0f : wz;
-        const float inv_wz = __fdiv_rn(1.0f, wz);
-        const Query qu = make_query(qc / g.WW, qc % g.WW, g);
-        const int lr = qu.iy * g.W + qu.ix;
-        ws.par[lane][0] = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
-        ws.par[lane][1] = make_float4(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_), __int_as_float(lr), __int_as_float(live ? cnt_i : -1));
-      }
-      {
-        // the 16 lists of this warp are contiguous: copy them with coalesced 16-byte loads
-        const uint4* src = reinterpret_cast<const uint4*>(sc.bin_ent + ((size_t)b * qs + q_w) * kSlots);
-        uint4* dst = reinterpret_cast<uint4*>(&ws.ent[0][0]);
-#pragma unroll
-        for (int i = 0; i < kGatherDests / 4; ++i) {
-          const int idx = i * 32 + lane;
-          dst[idx] = (q_w + (idx >> 3) < qs) ? __ldg(src + idx) : make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-      __syncwarp();
-      TRACE_EPI(c, 5);
-      // ---- cooperative gather: one destination at a time, lane = channel pair, next destination's rows in flight ----
-      {
-        float2 ya[8], yb[8], ra, rb2;
-        issue(0, ya, ra);
-#pragma unroll 1
-        for (int j = 0; j < kGatherDests; j += 2) {
-          issue(j + 1, yb, rb2);
-          finish(j, q_w, ya, ra);
-          if (j + 2 < kGatherDests) issue(j + 2, ya, ra);
-          finish(j + 1, q_w, yb, rb2);
-        }
-      }
-      __syncwarp();
-      fence_proxy_async_smem();
-      mbar_arrive(&sm.bars.a_ready[c.tile]);
-      TRACE_EPI(c, 6);
-      // ---- layers 1..3 and the output layer: thread = (pixel row, column half) ----
-      sine_epilogue(c, 0, s1, sm.consts, kColA, &sm.bars.a_ready[c.tile], false);
-      sine_epilogue(c, 0, s2, sm.consts + 64, kColA, &sm.bars.a_ready[c.tile], false);
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-      if (c.half == 0) o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) sine_out3_epilogue(c, ch & 1, s3, cw + 64 * ch, o0, o1, o2);
-      TRACE_EPI(c, 2);
-      combine_halves(sm, c, row, o0, o1, o2);
-      const int q = q_t + row;
-      if (q < qs && c.half == 0) {
-        float* out = rgb + ((size_t)(n * B + b) * 3) * qs + q;
-        out[0] = fminf(fmaxf(o0, 0.0f), 1.0f);
-        out[(size_t)qs] = fminf(fmaxf(o1, 0.0f), 1.0f);
-        out[(size_t)2 * qs] = fminf(fmaxf(o2, 0.0f), 1.0f);
-      }
-    }
-  }
-  teardown(tmem_base);
-}
-
-// ======================================================================================================
 // Destination gather of the three forward splats + blend + synth_net layer 0 (per timestamp), SIMT.
 // Split from the tensor-core kernel: the gather is a memory-latency problem (8 source rows of 256 B per destination on
 // average, two reference frames x four corners) that wants many warps and the whole L1, the MLP is an issue-slot
@@ -1317,17 +1032,45 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(256, 2) gather_l0_kernel(motif_geom_t g, int B, int N, int n, int b, float t, Scratch sc,
-                                                          float* __restrict__ dbg_pre0) {
+constexpr int kBandBlockRows = 4;  // block rows (of kGH destination rows) per L2 band
+
+// Grid = (timestamps of the group) x (32 x 8 destination blocks), ordered BAND-major: all timestamps of a band of
+// kBandBlockRows block rows run back to back, so the per-source rows Y they share (both reference frames, ~21 MB per
+// band at 1280 columns, plus the flow halo) are read from HBM by the first timestamp and from L2 by the others.
+// One warp = one image row of the block, TWO destinations at a time: half-warp <-> destination, lane <-> 4 channels
+// (one LDG.128 per list entry and lane, a half-warp reads one 256-byte source row).  All rows of a destination
+// (first 8 entries, then the rare 9..16) are requested back to back before the first is used; slots past the list
+// length are predicated off, never zero-filled.
+__global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, Scratch sc,
+                                                          float* __restrict__ dbg_pre0, int band_rows) {
   __shared__ uint2 ent_s[kGH][kGW][kSlots];  // the warp's 32 destination lists (4 KB per warp)
+  __shared__ float4 par_s[kGH][kGW][2];      // per-destination scalars (1 KB per warp)
+  __shared__ float4 rk_s[16][7];             // rank-1 layer-0 weights per 4-channel group (every warp writes the same values)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
   const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int blocks_x = (g.WW + kGW - 1) / kGW;
-  const int qy = ((int)blockIdx.x / blocks_x) * kGH + warp;
-  const int x0 = ((int)blockIdx.x % blocks_x) * kGW;
+  const int blocks_x = (g.WW + kGW - 1) / kGW, blocks_y = (g.HH + kGH - 1) / kGH;
+  int blk, nl;
+  {
+    const int per_band = band_rows * blocks_x;                  // blocks of one timestamp in a full band
+    const int full = (blocks_y / band_rows) * nt * per_band;    // blocks of all full bands
+    int bid = (int)blockIdx.x;
+    if (bid < full) {
+      const int band = bid / (nt * per_band), r = bid - band * nt * per_band;
+      nl = r / per_band;
+      blk = band * per_band + (r - nl * per_band);
+    } else {
+      const int last = (blocks_y % band_rows) * blocks_x;
+      bid -= full;
+      nl = bid / last;
+      blk = (blocks_y / band_rows) * per_band + (bid - nl * last);
+    }
+  }
+  const float t = time_of(times, nl);
+  const int qy = (blk / blocks_x) * kGH + warp;
+  const int x0 = (blk % blocks_x) * kGW;
   if (qy >= g.HH) return;  // whole warps only; no block-wide barrier below
   const int n_dest = min(kGW, g.WW - x0);
-  const size_t d0 = (size_t)b * qs + (size_t)qy * g.WW + x0;  // first destination of the warp
+  const size_t d0 = ((size_t)nl * B + b) * qs + (size_t)qy * g.WW + x0;  // first destination of the warp
   // ---- the 32 lists of the warp are contiguous (4 KB): asynchronous copy into shared memory ----
   {
     const uint4* src = reinterpret_cast<const uint4*>(sc.bin_ent + d0 * kSlots);
@@ -1339,21 +1082,22 @@ __global__ void __launch_bounds__(256, 2) gather_l0_kernel(motif_geom_t g, int B
       cp_async16(dst + idx, on ? src + idx : src, on);
     }
   }
-  // rank-1 input weights of this lane's two channels (4 l16 + 2 h, + 1), pre-scaled by 30:
+  // rank-1 input weights, pre-scaled by 30, in shared memory (read once per destination):
   // s_e0[ch] = (bias [in rtab], w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t, 0)
-  const int ch0 = 4 * l16 + 2 * h;
-  float rk[2][5], ct[2];
+  //   ->  rk_s[group][.] = 24 floats: per channel of the group (w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t t)
+  for (int idx = lane; idx < 16 * 6; idx += 32) {
+    const int grp = idx / 6, k = idx - grp * 6;
+    float v[4];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const float* e = sc.wpack + WeightPack::s_e0 + 8 * (ch0 + u);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) rk[u][i] = e[1 + i] * kOmega;
-    ct[u] = e[6] * t * kOmega;
+    for (int u = 0; u < 4; ++u) {
+      const int f = 4 * k + u, c = f / 6, i = f - c * 6;
+      const float* e = sc.wpack + WeightPack::s_e0 + 8 * (4 * grp + c);
+      v[u] = (i < 5 ? e[1 + i] : e[6] * t) * kOmega;
+    }
+    rk_s[grp][k] = make_float4(v[0], v[1], v[2], v[3]);
   }
   // ---- per-destination scalars (Ours.py:813-814, 826-829, 834), lane <-> destination; re-arm the accumulators ----
-  float4 pa;        // 1/wz, dx', dy', zmax
-  float2 pb;        // count/16, wz/count
-  int cnt_l, lr_l;  // list length (-1: outside the image), nearest LR latent
+  // par_s[j] = (1/wz, dx', dy', zmax), (count/16, wz/count, nearest LR latent [int], list length [int, -1: outside])
   {
     const bool live = lane < n_dest;
     const size_t d = d0 + (live ? lane : 0);
@@ -1375,85 +1119,87 @@ __global__ void __launch_bounds__(256, 2) gather_l0_kernel(motif_geom_t g, int B
     const float wz_ = wz == 1.0f ? 0.0f : wz;
     const float inv_wz = __fdiv_rn(1.0f, wz);
     const Query qu = make_query(qy, min(x0 + lane, g.WW - 1), g);
-    pa = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
-    pb = make_float2(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_));
-    cnt_l = live ? cnt_i : -1;
-    lr_l = qu.iy * g.W + qu.ix;
+    par_s[warp][lane][0] = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
+    par_s[warp][lane][1] = make_float4(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_), __int_as_float(qu.iy * g.W + qu.ix), __int_as_float(live ? cnt_i : -1));
   }
   cp_async_wait_all();
   __syncwarp();
 
-  const float4* Y4 = reinterpret_cast<const float4*>(sc.Y);
-  const float2* R2 = reinterpret_cast<const float2*>(sc.rtab + (size_t)b * P * 64);
-  const int bn = b * N + n;
-  uint32_t* a0_out = sc.a0 + ((size_t)b * gridDim.x * (kGW * kGH) + ((size_t)blockIdx.x * kGH + warp) * kGW) * 64;
+  const float4* Y4 = reinterpret_cast<const float4*>(sc.Y) + l16;
+  const float4* R4 = reinterpret_cast<const float4*>(sc.rtab + (size_t)b * P * 64) + l16;
+  const int bn = b * N + n0 + nl;
+  uint32_t* a0_out = sc.a0 + (((size_t)nl * B + b) * ((size_t)blocks_x * blocks_y) * (kGW * kGH) + ((size_t)blk * kGH + warp) * kGW) * 64;
 
-  // rows of destination j: entry 2 i + h for this half-warp, i = 0..7 (predicated on the list length)
-  auto issue = [&](int j, float4 (&y)[8], float2& rr) {
-    const int cnt = min(__shfl_sync(0xffffffffu, cnt_l, j), kSlots);
-    const int lr = __shfl_sync(0xffffffffu, lr_l, j);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t id = ent_s[warp][j][2 * i + h].x;
-      y[i] = (2 * i + h < cnt) ? __ldg(Y4 + (size_t)id * 16 + l16) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    rr = __ldg(R2 + ((size_t)lr * 64 + ch0) / 2);
-  };
-  auto finish = [&](int j, const float4 (&y)[8], const float2 rr) {
-    const int cnt_i = __shfl_sync(0xffffffffu, cnt_l, j);
+#pragma unroll 1
+  for (int it = 0; it < kGW / 2; ++it) {
+    const int j = 2 * it + h;  // this half-warp's destination
+    const float4 pa = par_s[warp][j][0], pb = par_s[warp][j][1];
+    const int cnt_i = __float_as_int(pb.w);
     const int cnt = min(cnt_i, kSlots);
+    const uint2* ent = ent_s[warp][j];
+    float4 y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < cnt) y[i] = __ldg(Y4 + (size_t)ent[i].x * 16);
+    const float4 rr = __ldg(R4 + (size_t)__float_as_int(pb.z) * 16);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float we = (2 * i + h < cnt) ? __uint_as_float(ent_s[warp][j][2 * i + h].y) : 0.0f;
-      acc.x = fmaf(we, y[i].x, acc.x);
-      acc.y = fmaf(we, y[i].y, acc.y);
-      acc.z = fmaf(we, y[i].z, acc.z);
-      acc.w = fmaf(we, y[i].w, acc.w);
+      if (i < cnt) {
+        const float we = __uint_as_float(ent[i].y);
+        acc.x = fmaf(we, y[i].x, acc.x);
+        acc.y = fmaf(we, y[i].y, acc.y);
+        acc.z = fmaf(we, y[i].z, acc.z);
+        acc.w = fmaf(we, y[i].w, acc.w);
+      }
     }
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+    if (__any_sync(0xffffffffu, cnt > 8)) {  // entries 9..16 of either destination
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (8 + i < cnt) y[i] = __ldg(Y4 + (size_t)ent[8 + i].x * 16);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (8 + i < cnt) {
+          const float we = __uint_as_float(ent[8 + i].y);
+          acc.x = fmaf(we, y[i].x, acc.x);
+          acc.y = fmaf(we, y[i].y, acc.y);
+          acc.z = fmaf(we, y[i].z, acc.z);
+          acc.w = fmaf(we, y[i].w, acc.w);
+        }
+      }
+    }
     const size_t d = d0 + j;
-    if (cnt_i > kSlots) {  // spilled contributions of an overfull list (warp-uniform branch)
+    if (cnt_i > kSlots) {  // spilled contributions of an overfull list
       float4* sp = reinterpret_cast<float4*>(sc.spill + d * 64) + l16;
       const float4 v = *sp;
       acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-      __syncwarp();
-      if (h == 0) *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+      *sp = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float inv_wz = __shfl_sync(0xffffffffu, pa.x, j), dxp = __shfl_sync(0xffffffffu, pa.y, j), dyp = __shfl_sync(0xffffffffu, pa.z, j);
-    const float zm = __shfl_sync(0xffffffffu, pa.w, j), c16 = __shfl_sync(0xffffffffu, pb.x, j), wzc = __shfl_sync(0xffffffffu, pb.y, j);
-    float pre[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const float lin = fmaf(rk[u][0], dxp, fmaf(rk[u][1], dyp, fmaf(rk[u][2], zm, fmaf(rk[u][3], c16, fmaf(rk[u][4], wzc, ct[u])))));
-      const float a = u == 0 ? (h ? acc.z : acc.x) : (h ? acc.w : acc.y);
-      pre[u] = fmaf(a, inv_wz, (u == 0 ? rr.x : rr.y) + lin);
+    if (cnt_i >= 0) {  // inside the image
+      // rk_s[l16] = per channel (w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t t), four channels back to back
+      const float4* rk = rk_s[l16];
+      const float4 k0 = rk[0], k1 = rk[1], k2 = rk[2], k3 = rk[3], k4 = rk[4], k5 = rk[5];
+      const float dxp = pa.y, dyp = pa.z, zm = pa.w, c16 = pb.x, wzc = pb.y;
+      const float lin0 = fmaf(k0.x, dxp, fmaf(k0.y, dyp, fmaf(k0.z, zm, fmaf(k0.w, c16, fmaf(k1.x, wzc, k1.y)))));
+      const float lin1 = fmaf(k1.z, dxp, fmaf(k1.w, dyp, fmaf(k2.x, zm, fmaf(k2.y, c16, fmaf(k2.z, wzc, k2.w)))));
+      const float lin2 = fmaf(k3.x, dxp, fmaf(k3.y, dyp, fmaf(k3.z, zm, fmaf(k3.w, c16, fmaf(k4.x, wzc, k4.y)))));
+      const float lin3 = fmaf(k4.z, dxp, fmaf(k4.w, dyp, fmaf(k5.x, zm, fmaf(k5.y, c16, fmaf(k5.z, wzc, k5.w)))));
+      const float pre0 = fmaf(acc.x, pa.x, rr.x + lin0), pre1 = fmaf(acc.y, pa.x, rr.y + lin1);
+      const float pre2 = fmaf(acc.z, pa.x, rr.z + lin2), pre3 = fmaf(acc.w, pa.x, rr.w + lin3);
+      if (dbg_pre0 != nullptr) {
+        float* dp = dbg_pre0 + ((size_t)bn * 64 + 4 * l16) * qs + (size_t)qy * g.WW + x0 + j;
+        dp[0] = pre0 * (1.0f / kOmega);
+        dp[qs] = pre1 * (1.0f / kOmega);
+        dp[2 * (size_t)qs] = pre2 * (1.0f / kOmega);
+        dp[3 * (size_t)qs] = pre3 * (1.0f / kOmega);
+      }
+      uint2 hi, lo;
+      split_pair(__sinf(pre0), __sinf(pre1), hi.x, lo.x);
+      split_pair(__sinf(pre2), __sinf(pre3), hi.y, lo.y);
+      uint2* o = reinterpret_cast<uint2*>(a0_out + (size_t)j * 64) + l16;
+      o[0] = hi;
+      o[16] = lo;
     }
-    if (cnt_i < 0) return;  // outside the image (warp-uniform)
-    if (dbg_pre0 != nullptr) {
-      const size_t dq = (size_t)qy * g.WW + x0 + j;
-      dbg_pre0[((size_t)bn * 64 + ch0) * qs + dq] = pre[0] * (1.0f / kOmega);
-      dbg_pre0[((size_t)bn * 64 + ch0 + 1) * qs + dq] = pre[1] * (1.0f / kOmega);
-    }
-    uint32_t hi, lo;
-    split_pair(__sinf(pre[0]), __sinf(pre[1]), hi, lo);
-    uint32_t* o = a0_out + (size_t)j * 64 + 2 * l16 + h;
-    o[0] = hi;
-    o[32] = lo;
-  };
-
-  float4 ya[8], yb[8];
-  float2 ra, rb2;
-  issue(0, ya, ra);
-#pragma unroll 1
-  for (int j = 0; j < kGW; j += 2) {
-    issue(j + 1, yb, rb2);
-    finish(j, ya, ra);
-    if (j + 2 < kGW) issue(j + 2, ya, ra);
-    finish(j + 1, yb, rb2);
   }
 }
 
@@ -1465,12 +1211,15 @@ using QSmemS = QSmem<6>;
 
 // consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) float4 per hidden unit (30 b3, w4[0], w4[1], w4[2])  [1152,1155) b4
 //         [1156] s1  [1157] s2  [1158] s3
-__global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, int B, int N, int n, int b, int n_items, Scratch sc, float* __restrict__ rgb) {
+// Work item = (timestamp of the group, 128 consecutive destinations in a-order), timestamp-major.
+__global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, int items_per_t, Scratch sc,
+                                                             float* __restrict__ rgb) {
   extern __shared__ unsigned char smem_raw[];
   QSmemS& sm = *reinterpret_cast<QSmemS*>(align1024(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qs = g.HH * g.WW;
   const int blocks_x = (g.WW + kGW - 1) / kGW;
+  const int n_items = nt * items_per_t;
   const float* wp = sc.wpack;
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
     sm.consts[i] = wp[WeightPack::s_b1 + i] * kOmega;
@@ -1503,14 +1252,15 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
     const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
     const int n_iters = q_iters(n_items, c.tile);
-    const uint4* a0 = reinterpret_cast<const uint4*>(sc.a0 + (size_t)b * n_items * 128 * 64);
     for (int it = 0; it < n_iters; ++it) {
       TRACE_Q(c, 1);
       const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
-      const int a = item * 128 + c.quad * 32 + lane;
+      const int nl = item / items_per_t;
+      const int n = n0 + nl;
+      const int a = (item - nl * items_per_t) * 128 + c.quad * 32 + lane;
       // layer-1 A operand: this row's 64 fp16 hi/lo pairs from the gather kernel
       {
-        const uint4* src = a0 + (size_t)a * 16;
+        const uint4* src = reinterpret_cast<const uint4*>(sc.a0) + (((size_t)nl * B + b) * items_per_t * 128 + a) * 16;
         uint4 v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __ldg(src + k);
@@ -1615,51 +1365,57 @@ int f16_set_trace(long long* buf, int capacity) {
   return 0;
 }
 
-size_t decode_f16_workspace_bytes(int B, int H, int W, int HH, int WW) {
+static int group_size(int N) { return N < f16::kMaxGroup ? (N > 0 ? N : 1) : f16::kMaxGroup; }
+
+size_t decode_f16_workspace_bytes(int B, int N, int H, int W, int HH, int WW) {
   size_t bytes = 0;
-  f16::layout(B, H, W, HH, WW, nullptr, nullptr, &bytes);
+  f16::layout(B, group_size(N), H, W, HH, WW, nullptr, nullptr, &bytes);
   return bytes;
 }
 
+// Three phases per group of up to kMaxGroup timestamps (all of a 7-timestamp Adobe clip): flow_imnet + binning of
+// every timestamp, then the destination gather of every timestamp in L2-band order, then synth_net of every
+// timestamp.  One launch each: the per-source rows are read from HBM once per group instead of once per timestamp.
 int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   using namespace f16;
   const motif_geom_t& g = a->geom;
   MOTIF_REQUIRE(2ull * g.B * g.HH * g.WW < (1ull << 32), "decode: 2*B*HH*WW must fit 32 bits");
+  const int NT = group_size(g.N);
   Scratch sc;
   size_t need = 0;
-  layout(g.B, g.H, g.W, g.HH, g.WW, &sc, (char*)a->workspace, &need);
+  layout(g.B, NT, g.H, g.W, g.HH, g.WW, &sc, (char*)a->workspace, &need);
   if (a->workspace_bytes < need) return fail(MOTIF_E_WORKSPACE, "decode: workspace %zu < %zu bytes", a->workspace_bytes, need);
   if (a->n_begin == a->n_end) return 0;
   MOTIF_REQUIRE(a->dbg_synth_in == nullptr, "decode: dbg_synth_in is only produced by precision fp32 / tf32x3 (f16x3 never forms the 198-channel input)");
   const size_t qs = (size_t)g.HH * g.WW;
-  const int smem_fq = (int)sizeof(QSmemF) + 1024;
-  static const bool old_flow = getenv("MOTIF_FLOW_OLD") != nullptr;
-  static const bool old_synth = getenv("MOTIF_SYNTH_OLD") != nullptr;
-  const int smem_sq = (int)sizeof(QSmemS) + 1024;
+  const int smem_fq = (int)sizeof(QSmemF) + 1024, smem_sq = (int)sizeof(QSmemS) + 1024, smem_i = (int)sizeof(SmemI) + 1024;
   const int g_blocks = ceil_div(g.WW, kGW) * ceil_div(g.HH, kGH);
-  const int smem_i = (int)sizeof(SmemI) + 1024, smem_f = (int)sizeof(SmemF) + 1024, smem_s = (int)sizeof(SmemS) + 1024;
   static bool attr_done = false;
   static int n_sm = 148;
   if (!attr_done) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
-    MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sq));
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 32));
-    MOTIF_CUDA(cudaFuncSetAttribute(synth_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 75));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
     MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     attr_done = true;
   }
+  // arm the destination accumulators (a no-op when the previous decode on this workspace completed, see arm_kernel)
+  Magic magic, none;
+  magic.w[0] = 0x4d6f5449u, magic.w[1] = ((uint32_t)g.B << 16) ^ (uint32_t)NT ^ 0x9e3779b9u;
+  magic.w[2] = (uint32_t)g.HH, magic.w[3] = (uint32_t)g.WW;
+  none.w[0] = none.w[1] = none.w[2] = none.w[3] = 0u;
+  arm_kernel<<<n_sm * 8, 256, 0, st>>>(sc.armed, magic, reinterpret_cast<uint4*>(sc.side), sc.zero_bytes / 16, sc.zmax, (size_t)NT * g.B * qs);
+  MOTIF_LAUNCHED("arm_kernel");
+  mark_kernel<<<1, 32, 0, st>>>(sc.armed, none);
+  MOTIF_LAUNCHED("mark_kernel");
   if (int rc = prepare(a, sc, st)) return rc;
-  MOTIF_CUDA(cudaMemsetAsync(sc.side, 0, sizeof(float) * g.B * qs * 4, st));
-  MOTIF_CUDA(cudaMemsetAsync(sc.bin_count, 0, sizeof(int) * g.B * qs, st));
-  MOTIF_CUDA(cudaMemsetAsync(sc.spill, 0, sizeof(float) * g.B * qs * 64, st));
-  fill_kernel<<<148 * 8, 256, 0, st>>>(sc.zmax, 1.0f, (size_t)g.B * qs);
-  MOTIF_LAUNCHED("fill_kernel");
-  const int tiles128 = ceil_div((long long)qs, 128), units256 = ceil_div((long long)qs, 256);
-  const int grid128 = tiles128 < n_sm ? tiles128 : n_sm, grid256 = units256 < n_sm ? units256 : n_sm;
+  const int tiles128 = ceil_div((long long)qs, 128);
+  const int grid128 = tiles128 < n_sm ? tiles128 : n_sm;
   for (int b = 0; b < g.B; ++b) {
     {
       if (int rc = trace_select(0, st)) return rc;
@@ -1667,38 +1423,35 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       imnet_f16_kernel<<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc);
       MOTIF_LAUNCHED("imnet_f16_kernel");
     }
-    for (int n = a->n_begin; n < a->n_end; ++n) {
-      const float t = a->target_t[b * g.N + n];
+    for (int n0 = a->n_begin; n0 < a->n_end; n0 += NT) {
+      const int nt = a->n_end - n0 < NT ? a->n_end - n0 : NT;
+      Times times;
+      for (int i = 0; i < kMaxGroup; ++i) times.t[i] = i < nt ? a->target_t[b * g.N + n0 + i] : 0.0f;
       {
         if (int rc = trace_select(1, st)) return rc;
         ProfScope prof("flow_bin_f16_kernel", st);
-        if (old_flow) {
-          flow_bin_f16_kernel<<<grid128, kThreads, smem_f, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
-        } else {
-          const int groups = ceil_div(2LL * tiles128, 4);
-          flow_bin_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n, b, t, a->alpha, sc, a->flow_out);
-        }
+        const int groups = ceil_div((long long)nt * 2 * tiles128, 4);
+        flow_bin_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n0, nt, b, times, a->alpha, sc, a->flow_out);
         MOTIF_LAUNCHED("flow_bin_f16_kernel");
       }
-      if (old_synth) {
+      {
+        ProfScope prof("gather_l0_kernel", st);
+        static const int band_rows = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : kBandBlockRows;
+        static const int dsmem = getenv("MOTIF_GATHER_DSMEM") ? atoi(getenv("MOTIF_GATHER_DSMEM")) : 0;
+        gather_l0_kernel<<<nt * g_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows);
+        MOTIF_LAUNCHED("gather_l0_kernel");
+      }
+      {
         if (int rc = trace_select(2, st)) return rc;
         ProfScope prof("synth_f16_kernel", st);
-        synth_f16_kernel<<<grid256, kThreads, smem_s, st>>>(g, g.B, g.N, n, b, t, sc, a->rgb, a->dbg_pre0);
-        MOTIF_LAUNCHED("synth_f16_kernel");
-      } else {
-        {
-          ProfScope prof("gather_l0_kernel", st);
-          gather_l0_kernel<<<g_blocks, 256, 0, st>>>(g, g.B, g.N, n, b, t, sc, a->dbg_pre0);
-          MOTIF_LAUNCHED("gather_l0_kernel");
-        }
-        if (int rc = trace_select(2, st)) return rc;
-        ProfScope prof("synth_f16_kernel", st);
-        const int items = 2 * g_blocks, groups = ceil_div(items, 4);
-        synth_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_sq, st>>>(g, g.B, g.N, n, b, items, sc, a->rgb);
+        const int items_per_t = 2 * g_blocks, groups = ceil_div((long long)nt * items_per_t, 4);
+        synth_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_sq, st>>>(g, g.B, g.N, n0, nt, b, items_per_t, sc, a->rgb);
         MOTIF_LAUNCHED("synth_f16_kernel");
       }
     }
   }
+  mark_kernel<<<1, 32, 0, st>>>(sc.armed, magic);
+  MOTIF_LAUNCHED("mark_kernel");
   return 0;
 }
 

@@ -557,6 +557,6 @@ extern "C" size_t motif_decode_workspace_bytes(int B, int N, int H, int W, int H
   if (B <= 0 || N <= 0 || H <= 0 || W <= 0 || HH <= 0 || WW <= 0) return 0;
   size_t bytes = 0;
   decode_layout(B, N, H, W, HH, WW, nullptr, nullptr, &bytes);
-  const size_t b16 = decode_f16_workspace_bytes(B, H, W, HH, WW);  // one workspace serves every precision
+  const size_t b16 = decode_f16_workspace_bytes(B, N, H, W, HH, WW);  // one workspace serves every precision
   return bytes > b16 ? bytes : b16;
 }

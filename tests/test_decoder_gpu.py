@@ -205,3 +205,33 @@ def test_state_dict_loader_accepts_full_checkpoint_layout():
     assert dec.alpha == -20.0
     with pytest.raises(KeyError):
         SpaceTimeDecoder({k: v for k, v in params.items() if "synth_net.net.4" not in k})
+
+
+def test_f16x3_timestamp_groups_and_rearmed_workspace():
+    """x12-time shape (11 timestamps > one group of 8, BASELINE config 3): the grouped three-phase decode against the
+    oracle; then the SAME decoder object again (accumulators re-armed by their consumer, no clear), after a decode of
+    another precision and of another geometry scribbled over the shared workspace."""
+    gen = torch.Generator().manual_seed(13)
+    B, H, W, HH, WW = 1, 10, 12, 35, 42          # x3.5 space
+    feat = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    ff = torch.randn(2 * B, 64, H, W, generator=gen) * 0.3
+    res = torch.randn(B, 64, H, W, generator=gen) * 0.3
+    tt = torch.tensor([[k / 12 for k in range(1, 12)]])
+    N = tt.shape[1]
+    params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
+    r_rgb, r_flow = decoder_ref.decode(feat, ff, res, tt, HH, WW, params)
+    dec = _decoder(params, "f16x3")
+    args = (feat.cuda(), ff.cuda(), res.cuda(), tt, (HH, WW))
+    rgb1, flow1 = dec.decode(*args)
+    assert (flow1.cpu() - r_flow).abs().max().item() < FLOW_TOL
+    d_rgb, p, _ = _compare_frames(rgb1.cpu(), r_rgb, r_flow, HH / H, B, N)
+    assert d_rgb < TOL and p > PSNR_MIN, (d_rgb, p)
+    rgb2, _ = dec.decode(*args)                                   # armed workspace: must be bit-identical
+    assert (rgb1 - rgb2).abs().max().item() < 1e-5            # list order (atomic slot order) may differ: not bit-identical
+    dec.decode(*args, precision="tf32x3")                         # another layout scribbles over the workspace
+    dec.decode(feat.cuda()[..., :8, :8].contiguous(), ff.cuda()[..., :8, :8].contiguous(), res.cuda()[..., :8, :8].contiguous(),
+               tt[:, :3], (16, 24))                               # another geometry
+    rgb3, _ = dec.decode(*args)
+    assert (rgb1 - rgb3).abs().max().item() < 1e-5
+    part, _ = dec.decode(*args, n_range=(6, 10))                  # a range that straddles the group boundary
+    assert (part[6:10] - rgb1[6:10]).abs().max().item() < 1e-5

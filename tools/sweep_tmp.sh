@@ -1,0 +1,10 @@
+run() { echo "== $*"; env "$@" python bench.py --no-cpu-baseline --steps 10 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print(round(d['ms_per_step'],3), {k: round(v['avg_ms'],3) for k,v in d['kernels'].items()})"; }
+python -m pytest tests/test_decoder_gpu.py -m gpu -x -q 2>&1 | tail -3
+run A=1
+run MOTIF_GATHER_CARVEOUT=60
+run MOTIF_GATHER_CARVEOUT=50
+run MOTIF_GATHER_DSMEM=32768 MOTIF_GATHER_CARVEOUT=50
+run MOTIF_GATHER_BAND=90
