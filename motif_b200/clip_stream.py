@@ -1,0 +1,101 @@
+"""Host-buffer front end of the decoder: a double-buffered clip pipeline.
+
+``SpaceTimeDecoder.decode`` works on resident device tensors.  A caller that holds the LR latents in
+host memory (the encoder ran elsewhere, or clips are streamed from disk) pays a host->device copy
+of 320*H*W*4 bytes and a device->host copy of 12 bytes per output pixel-timestamp per clip -- at
+Adobe240 size 1.4 ms each way over PCIe against ~7 ms of decode.  ``ClipStream`` overlaps them
+with the decode of the neighbouring clips: three CUDA streams (copy-in, compute, copy-out), two
+sets of device buffers, events between them.  Every clip's copies are issued by ``submit`` itself
+(nothing is cached across clips); ``synchronize`` waits for everything submitted so far.
+
+With ``torch.distributed`` initialised and ``world_size > 1`` the source rank copies the latents
+in and they are broadcast (the path's one exchange, ``sharding.broadcast_latents``) on the compute
+stream of every rank before its timestamps are decoded.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import sharding
+from .decoder import SpaceTimeDecoder
+
+
+class ClipStream:
+    def __init__(self, decoder: SpaceTimeDecoder, depth: int = 2, distributed: bool = False, src: int = 0, group=None):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.dec = decoder
+        self.dev = decoder.device
+        self.depth = depth
+        self.distributed = distributed
+        self.src = src
+        self.group = group
+        self.s_in = torch.cuda.Stream(self.dev)
+        self.s_out = torch.cuda.Stream(self.dev)
+        self._slots = [None] * depth
+        self._k = 0
+
+    def _slot(self, k, shapes, out_shape):
+        i = k % self.depth
+        sl = self._slots[i]
+        if sl is None or sl["shapes"] != shapes or sl["out"].shape != out_shape:
+            sl = {"shapes": shapes,
+                  "lat": [torch.empty(s, dtype=torch.float32, device=self.dev) for s in shapes],
+                  "out": torch.empty(out_shape, dtype=torch.float32, device=self.dev),
+                  "ev_in": torch.cuda.Event(), "ev_free": None, "ev_done": torch.cuda.Event(), "ev_out": None}
+            self._slots[i] = sl
+        return sl
+
+    def submit(self, feat_h: Optional[torch.Tensor], flow_feat_h: Optional[torch.Tensor], residual_h: Optional[torch.Tensor],
+               target_t, hr_size: Tuple[int, int], out_h: Optional[torch.Tensor], n_range: Optional[Tuple[int, int]] = None,
+               shapes: Optional[Sequence[Tuple[int, ...]]] = None):
+        """Queue one clip.  ``feat_h`` / ``flow_feat_h`` / ``residual_h``: pinned host tensors (on ranks other
+        than ``src`` of a distributed stream pass ``None`` and the three ``shapes``).  ``out_h``: pinned host tensor
+        ``[n_end - n_begin, B, 3, HH, WW]`` receiving this rank's frames (or ``None`` to leave them on the device).
+        Returns the device frame buffer ``[N, B, 3, HH, WW]`` of this slot (valid until the slot is reused)."""
+        import torch.distributed as dist
+
+        is_src = (not self.distributed) or dist.get_rank(self.group) == self.src
+        if is_src:
+            shapes = tuple(tuple(t.shape) for t in (feat_h, flow_feat_h, residual_h))
+        elif shapes is None:
+            raise ValueError("non-source ranks must pass the latent shapes")
+        shapes = tuple(tuple(s) for s in shapes)
+        tt = torch.as_tensor(target_t, dtype=torch.float32).reshape(shapes[2][0], -1)
+        B, N = tt.shape
+        HH, WW = int(hr_size[0]), int(hr_size[1])
+        n0, n1 = (0, N) if n_range is None else n_range
+        sl = self._slot(self._k, shapes, (N, B, 3, HH, WW))
+        self._k += 1
+        compute = torch.cuda.current_stream(self.dev)
+        if is_src:
+            with torch.cuda.stream(self.s_in):
+                if sl["ev_free"] is not None:
+                    self.s_in.wait_event(sl["ev_free"])        # the decode that last read these buffers has finished
+                for dst, src_t in zip(sl["lat"], (feat_h, flow_feat_h, residual_h)):
+                    dst.copy_(src_t, non_blocking=True)
+                sl["ev_in"].record(self.s_in)
+            compute.wait_event(sl["ev_in"])
+        if sl["ev_out"] is not None:
+            compute.wait_event(sl["ev_out"])                   # the copy-out that last read this frame buffer has finished
+        lat = sl["lat"]
+        if self.distributed:
+            lat = sharding.broadcast_latents(*lat, src=self.src, group=self.group)
+        self.dec.decode(lat[0], lat[1], lat[2], tt, (HH, WW), n_range=(n0, n1), return_flow=False, out=sl["out"])
+        sl["ev_done"].record(compute)
+        sl["ev_free"] = sl["ev_done"]
+        if out_h is not None and n1 > n0:
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(sl["ev_done"])
+                out_h[: n1 - n0].copy_(sl["out"][n0:n1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.s_out)
+                sl["ev_out"] = ev
+        return sl["out"]
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.s_in.synchronize()
+        self.s_out.synchronize()

@@ -697,6 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 // Per tile 128 TMEM columns: [0,32) A_hi [32,64) A_lo [64,128) D.  A single accumulator suffices: the epilogue
 // copies all 64 columns into registers and releases D at once, so the next block's MMAs overlap its arithmetic.
 // ======================================================================================================
+__device__ int g_issuer_mode = 0;  // tuning: 0 = one issuer warp for the four tiles, 1 = an issuer warp per tile
 constexpr int kQTileCols = 128;
 constexpr uint32_t kQColA = 0, kQColD = 64;
 
@@ -780,6 +781,57 @@ __device__ __forceinline__ void q_issuer(QBars& bars, const unsigned char* img_b
       }
       __syncwarp();
     }
+  }
+}
+
+// ONE issuer warp serves the four tiles: it polls their hand-off barriers in turn and issues the 12 MMAs of whichever
+// block is ready as one uninterrupted burst.  With an issuer per tile the four bursts interleave in the tensor queue
+// whenever the tiles are in phase, every block then completes at the END of the combined burst, all four epilogues
+// start together and fight for the same MUFU pipes while the tensor pipe idles: the tiles stay in lock step and tensor
+// and MUFU time add up instead of overlapping.  Block-granular FIFO service breaks the lock step: the first tile leaves
+// for its epilogue while the others are still queued.
+template <int tile, int NSTEPS>
+__device__ __forceinline__ bool q_poll_tile(QBars& bars, uint64_t img_desc, const QStep (&prog)[NSTEPS], int& s, uint32_t& ph_a, uint32_t& ph_f) {
+  constexpr uint32_t idesc = idesc_f16(128, 64);
+  constexpr uint32_t acol = tile * kQTileCols + kQColA, dcol = tile * kQTileCols + kQColD;
+  const QStep st = prog[s];
+  uint64_t* bar = st.wait == 1 ? &bars.a_ready[tile] : &bars.d_free[tile];
+  const uint32_t parity = st.wait == 1 ? ph_a : ph_f;
+  if (!__any_sync(0xffffffffu, mbar_test(bar, parity))) return false;
+  if (st.wait == 1) ph_a ^= 1; else ph_f ^= 1;
+  tc_fence_after();
+  const uint64_t bhi = img_desc + (uint64_t)(st.img * (kBlkBytes >> 4));
+  const uint64_t blo = bhi + (kBlkHalf >> 4);
+  if (elect_one()) {
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+      const uint32_t a = (term == 1) ? acol + 32 : acol;
+      const uint64_t b = (term == 2) ? blo : bhi;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) mma_f16_ts(dcol, a + ks * 8, b + 2 * ks, idesc, (term | ks) != 0);
+    }
+    mma_commit(&bars.d_ready[tile]);
+  }
+  __syncwarp();
+  s = s + 1 == NSTEPS ? 0 : s + 1;
+  return true;
+}
+
+template <int NSTEPS>
+__device__ __forceinline__ void q_issuer_all(QBars& bars, const unsigned char* img_base, const QStep (&prog)[NSTEPS], int n_items) {
+  const uint64_t img_desc = smem_desc_sw128(smem_u32(img_base));
+  int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  uint32_t pa0 = 0, pa1 = 0, pa2 = 0, pa3 = 0, pf0 = 0, pf1 = 0, pf2 = 0, pf3 = 0;
+  // blocks left per tile
+  int r0 = q_iters(n_items, 0) * NSTEPS, r1 = q_iters(n_items, 1) * NSTEPS, r2 = q_iters(n_items, 2) * NSTEPS, r3 = q_iters(n_items, 3) * NSTEPS;
+  mbar_wait(&bars.w_full, 0);
+  while ((r0 | r1 | r2 | r3) != 0) {
+    bool any = false;
+    if (r0 != 0 && q_poll_tile<0>(bars, img_desc, prog, s0, pa0, pf0)) --r0, any = true;
+    if (r1 != 0 && q_poll_tile<1>(bars, img_desc, prog, s1, pa1, pf1)) --r1, any = true;
+    if (r2 != 0 && q_poll_tile<2>(bars, img_desc, prog, s2, pa2, pf2)) --r2, any = true;
+    if (r3 != 0 && q_poll_tile<3>(bars, img_desc, prog, s3, pa3, pf3)) --r3, any = true;
+    if (!any) __nanosleep(40);
   }
 }
 
@@ -918,13 +970,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       for (int i = 0; i < 5; ++i) bulk_g2s(&sm.img[i][0], sc.wimg + (size_t)(kImgF1 + i) * kBlkBytes, kBlkBytes, &sm.bars.w_full);
     }
     __syncwarp();
-    q_issuer<0>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 0));
+    if (g_issuer_mode == 0) q_issuer_all(sm.bars, &sm.img[0][0], kQProgF, n_items);
+    else q_issuer<0>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 0));
   } else if (warp == 1) {
-    q_issuer<1>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 1));
+    if (g_issuer_mode != 0) q_issuer<1>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 1));
   } else if (warp == 2) {
-    q_issuer<2>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 2));
+    if (g_issuer_mode != 0) q_issuer<2>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 2));
   } else if (warp == 3) {
-    q_issuer<3>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 3));
+    if (g_issuer_mode != 0) q_issuer<3>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 3));
   } else {
     QEpi c = q_make_epi(sm.bars);
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
@@ -1240,13 +1293,14 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
       for (int i = 0; i < 6; ++i) bulk_g2s(&sm.img[i][0], sc.wimg + (size_t)(kImgS1 + i) * kBlkBytes, kBlkBytes, &sm.bars.w_full);
     }
     __syncwarp();
-    q_issuer<0>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 0));
+    if (g_issuer_mode == 0) q_issuer_all(sm.bars, &sm.img[0][0], kQProgS, n_items);
+    else q_issuer<0>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 0));
   } else if (warp == 1) {
-    q_issuer<1>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 1));
+    if (g_issuer_mode != 0) q_issuer<1>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 1));
   } else if (warp == 2) {
-    q_issuer<2>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 2));
+    if (g_issuer_mode != 0) q_issuer<2>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 2));
   } else if (warp == 3) {
-    q_issuer<3>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 3));
+    if (g_issuer_mode != 0) q_issuer<3>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 3));
   } else {
     QEpi c = q_make_epi(sm.bars);
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
@@ -1397,11 +1451,19 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sq));
     MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 75));
+                                    getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 50));
     MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
     MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (getenv("MOTIF_MBAR_HINT")) {
+      const uint32_t hint = (uint32_t)atoi(getenv("MOTIF_MBAR_HINT"));
+      MOTIF_CUDA(cudaMemcpyToSymbol(tc::c_mbar_hint, &hint, sizeof(hint)));
+    }
+    if (getenv("MOTIF_ISSUER_MODE")) {
+      const int mode = atoi(getenv("MOTIF_ISSUER_MODE"));
+      MOTIF_CUDA(cudaMemcpyToSymbol(g_issuer_mode, &mode, sizeof(int)));
+    }
     attr_done = true;
   }
   // arm the destination accumulators (a no-op when the previous decode on this workspace completed, see arm_kernel)

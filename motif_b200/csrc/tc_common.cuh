@@ -23,6 +23,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~the hint
 // elapses, instead of burning issue slots that the working warps of the same scheduler need.
+static __constant__ uint32_t c_mbar_hint = 100000u;  // per translation unit; tuning hook
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -30,7 +31,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(c_mbar_hint)
+      : "memory");
+  return ok != 0;
+}
+// Non-blocking test: has the phase with the given parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }

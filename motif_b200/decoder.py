@@ -160,11 +160,12 @@ class SpaceTimeDecoder:
         debug_synth_in: bool = False,
         precision: Optional[str] = None,
         debug_pre0: bool = False,
+        out: Optional[torch.Tensor] = None,
     ):
         """``Ours.py:659-858``.  Returns ``(rgb [N,B,3,HH,WW] in [0,1], flow_out [2BN,2,HH,WW] or None)``
         (plus the ``[B*N,198,HH,WW]`` synth_net input when ``debug_synth_in`` -- precisions ``fp32`` / ``tf32x3`` --
         or the ``[B*N,64,HH,WW]`` layer-0 pre-activation of synth_net when ``debug_pre0`` -- precision ``f16x3``,
-        which never forms the 198-channel input)."""
+        which never forms the 198-channel input).  ``out``: optional preallocated frame buffer (``ClipStream``)."""
         lib = _lib.load()
         for nm, t in (("feat", feat), ("flow_feat", flow_feat), ("residual", residual)):
             _lib.require_cuda_f32(nm, t, 4)
@@ -182,7 +183,12 @@ class SpaceTimeDecoder:
             featp = self.pack_latents(feat)
             ffp = self.pack_latents(flow_feat)
             resp = self.pack_latents(residual)
-            rgb = torch.empty(N, B, 3, HH, WW, dtype=torch.float32, device=dev)
+            if out is not None:
+                if out.shape != (N, B, 3, HH, WW) or out.dtype != torch.float32 or out.device != residual.device or not out.is_contiguous():
+                    raise ValueError(f"out must be a contiguous fp32 [{N},{B},3,{HH},{WW}] tensor on {dev}")
+                rgb = out
+            else:
+                rgb = torch.empty(N, B, 3, HH, WW, dtype=torch.float32, device=dev)
             flow_out = torch.empty(2 * B * N, 2, HH, WW, dtype=torch.float32, device=dev) if return_flow else None
             dbg = torch.zeros(B * N, 198, HH, WW, dtype=torch.float32, device=dev) if debug_synth_in else None
             pre0 = torch.zeros(B * N, 64, HH, WW, dtype=torch.float32, device=dev) if debug_pre0 else None

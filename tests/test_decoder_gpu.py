@@ -235,3 +235,26 @@ def test_f16x3_timestamp_groups_and_rearmed_workspace():
     assert (rgb1 - rgb3).abs().max().item() < 1e-5
     part, _ = dec.decode(*args, n_range=(6, 10))                  # a range that straddles the group boundary
     assert (part[6:10] - rgb1[6:10]).abs().max().item() < 1e-5
+
+
+def test_clip_stream_matches_resident_decode():
+    """Host-buffer front end (double-buffered copy-in / decode / copy-out): five different clips through two slots
+    give the frames of the plain resident decode of each clip, in order."""
+    from motif_b200.clip_stream import ClipStream
+
+    gen = torch.Generator().manual_seed(17)
+    B, H, W, HH, WW = 1, 12, 16, 48, 64
+    params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
+    dec = _decoder(params, "f16x3")
+    tt = torch.tensor([[0.25, 0.5, 0.75]])
+    clips, outs = [], []
+    for _ in range(5):
+        clips.append([(torch.randn(s, generator=gen) * 0.3).pin_memory() for s in ((2 * B, 64, H, W), (2 * B, 64, H, W), (B, 64, H, W))])
+        outs.append(torch.zeros(2, B, 3, HH, WW).pin_memory())
+    cs = ClipStream(dec, depth=2)
+    for c, o in zip(clips, outs):
+        cs.submit(c[0], c[1], c[2], tt, (HH, WW), o, n_range=(1, 3))
+    cs.synchronize()
+    for c, o in zip(clips, outs):
+        ref, _ = dec.decode(c[0].cuda(), c[1].cuda(), c[2].cuda(), tt, (HH, WW), return_flow=False)
+        assert (o - ref[1:3].cpu()).abs().max().item() < 1e-5
