@@ -502,11 +502,38 @@ __device__ __forceinline__ void ld_half(Epi& c, int dbuf, uint32_t (&r)[32]) {
   tmem_wait_ld();
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2: two IEEE fp32 operations per issued instruction; each lane rounds exactly
+// like the scalar instruction).  The epilogues are issue-slot bound, so pairing the per-element FFMAs is a direct win.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fsub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // fp32 pair -> fp16 hi pair + fp16 lo pair (lo = fp16 of the exact fp32 remainder)
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(__fsub_rn(a, f.x), __fsub_rn(b, f.y));
+  float ra, rb;
+  unpack2(fsub2(pack2(a, b), pack2(f.x, f.y)), ra, rb);
+  const __half2 l = __floats2half2_rn(ra, rb);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -697,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 // Per tile 128 TMEM columns: [0,32) A_hi [32,64) A_lo [64,128) D.  A single accumulator suffices: the epilogue
 // copies all 64 columns into registers and releases D at once, so the next block's MMAs overlap its arithmetic.
 // ======================================================================================================
-__device__ int g_issuer_mode = 0;  // tuning: 0 = one issuer warp for the four tiles, 1 = an issuer warp per tile
+__device__ int g_issuer_mode = 1;  // tuning: 1 = an issuer warp per tile (default, measured 1.5% faster), 0 = one polling issuer warp for the four tiles
 constexpr int kQTileCols = 128;
 constexpr uint32_t kQColA = 0, kQColD = 64;
 
@@ -874,24 +901,28 @@ __device__ __forceinline__ void q_publish(QEpi& c) {
   mbar_arrive(&c.bars->a_ready[c.tile]);
   TRACE_Q(c, 20);
 }
-// First layer from the LR table: v = sin(P0'[row] + e.x + e.y * rel_y + e.z * rel_x) (everything pre-scaled by 30)
-__device__ __forceinline__ void q_table_layer0(QEpi& c, const float* __restrict__ p0row, const float4* __restrict__ e0, float rel_y, float rel_x) {
-  const float4* src = reinterpret_cast<const float4*>(p0row);
-  float4 p[16];
+// First layer from the LR table: v = sin(P0'[row] + e.x + e.y * rel_y + e.z * rel_x) (everything pre-scaled by 30).
+// e0p: per PAIR of units (2p, 2p+1) two float4: (ex, ex', ey, ey'), (ez, ez', 0, 0).
+__device__ __forceinline__ void q_table_layer0(QEpi& c, const float* __restrict__ p0row, const float4* __restrict__ e0p, float rel_y, float rel_x) {
+  const ulonglong2* src = reinterpret_cast<const ulonglong2*>(p0row);
+  ulonglong2 p[16];
 #pragma unroll
   for (int j4 = 0; j4 < 16; ++j4) p[j4] = __ldg(src + j4);
+  const f32x2 ry2 = pack2(rel_y, rel_y), rx2 = pack2(rel_x, rel_x);
+  const ulonglong2* e2 = reinterpret_cast<const ulonglong2*>(e0p);
 #pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 16) {
     float v[16];
 #pragma unroll
-    for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 pp = p[(c0 >> 2) + j4];
-      const float pv[4] = {pp.x, pp.y, pp.z, pp.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 e = e0[c0 + 4 * j4 + u];
-        v[4 * j4 + u] = __sinf(pv[u] + fmaf(e.z, rel_x, fmaf(e.y, rel_y, e.x)));
-      }
+    for (int pr = 0; pr < 8; ++pr) {  // pair of units c0 + 2 pr, + 1
+      const int gp = (c0 >> 1) + pr;
+      const ulonglong2 ea = e2[2 * gp], eb = e2[2 * gp + 1];
+      const f32x2 pv = (pr & 1) ? p[gp >> 1].y : p[gp >> 1].x;
+      const f32x2 arg = fadd2(pv, ffma2(eb.x, rx2, ffma2(ea.y, ry2, ea.x)));
+      float a0, a1;
+      unpack2(arg, a0, a1);
+      v[2 * pr] = __sinf(a0);
+      v[2 * pr + 1] = __sinf(a1);
     }
     split_store16(c.lane_addr + kQColA + c0 / 2, v);
   }
@@ -901,38 +932,51 @@ __device__ __forceinline__ void q_table_layer0(QEpi& c, const float* __restrict_
 __device__ __forceinline__ void q_sine_epilogue(QEpi& c, float s, const float* __restrict__ cb) {
   uint32_t r[64];
   q_take_d(c, r, false);
+  const f32x2 s2 = pack2(s, s);
 #pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 16) {
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
-      const float4 b = *reinterpret_cast<const float4*>(cb + c0 + 4 * j4);
-      v[4 * j4 + 0] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 0]), s, b.x));
-      v[4 * j4 + 1] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 1]), s, b.y));
-      v[4 * j4 + 2] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 2]), s, b.z));
-      v[4 * j4 + 3] = __sinf(fmaf(__uint_as_float(r[c0 + 4 * j4 + 3]), s, b.w));
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(cb + c0 + 4 * j4);
+      float a0, a1, a2, a3;
+      unpack2(ffma2(pack2(__uint_as_float(r[c0 + 4 * j4 + 0]), __uint_as_float(r[c0 + 4 * j4 + 1])), s2, b.x), a0, a1);
+      unpack2(ffma2(pack2(__uint_as_float(r[c0 + 4 * j4 + 2]), __uint_as_float(r[c0 + 4 * j4 + 3])), s2, b.y), a2, a3);
+      v[4 * j4 + 0] = __sinf(a0);
+      v[4 * j4 + 1] = __sinf(a1);
+      v[4 * j4 + 2] = __sinf(a2);
+      v[4 * j4 + 3] = __sinf(a3);
     }
     split_store16(c.lane_addr + kQColA + c0 / 2, v);
   }
   q_publish(c);
 }
-// 64 hidden units of a 64 -> 256 sine-layer chunk, followed by the 256 -> 3 linear layer on CUDA cores.
-// cw[j] = (30 * bias_j, w_out[0][j], w_out[1][j], w_out[2][j]) (smem, the chunk's 64 units)
+// 64 hidden units of a 64 -> 256 sine-layer chunk, followed by the 256 -> 3 linear layer on CUDA cores, two units per
+// instruction.  cw: per PAIR of units (2p, 2p+1) two float4 (smem, the chunk's 32 pairs):
+//   (30 b, 30 b', w_out[0], w_out[0]'), (w_out[1], w_out[1]', w_out[2], w_out[2]')
 __device__ __forceinline__ void q_sine_out3(QEpi& c, float s, const float4* __restrict__ cw, bool release, float& o0, float& o1, float& o2) {
   uint32_t r[64];
   q_take_d(c, r, release);
-  float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+  const f32x2 s2 = pack2(s, s);
+  const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(cw);
+  f32x2 p0[2] = {0ull, 0ull}, p1[2] = {0ull, 0ull}, p2[2] = {0ull, 0ull};
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    const float4 w = cw[j];
-    const float v = __sinf(fmaf(__uint_as_float(r[j]), s, w.x));
-    p0[j & 3] = fmaf(v, w.y, p0[j & 3]);
-    p1[j & 3] = fmaf(v, w.z, p1[j & 3]);
-    p2[j & 3] = fmaf(v, w.w, p2[j & 3]);
+  for (int pr = 0; pr < 32; ++pr) {
+    const ulonglong2 wa = w2[2 * pr], wb = w2[2 * pr + 1];
+    float a0, a1;
+    unpack2(ffma2(pack2(__uint_as_float(r[2 * pr]), __uint_as_float(r[2 * pr + 1])), s2, wa.x), a0, a1);
+    const f32x2 v = pack2(__sinf(a0), __sinf(a1));
+    p0[pr & 1] = ffma2(v, wa.y, p0[pr & 1]);
+    p1[pr & 1] = ffma2(v, wb.x, p1[pr & 1]);
+    p2[pr & 1] = ffma2(v, wb.y, p2[pr & 1]);
   }
-  o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
-  o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
-  o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+  float x0, x1, x2, x3;
+  unpack2(p0[0], x0, x1), unpack2(p0[1], x2, x3);
+  o0 += (x0 + x1) + (x2 + x3);
+  unpack2(p1[0], x0, x1), unpack2(p1[1], x2, x3);
+  o1 += (x0 + x1) + (x2 + x3);
+  unpack2(p2[0], x0, x1), unpack2(p2[1], x2, x3);
+  o2 += (x0 + x1) + (x2 + x3);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -940,8 +984,8 @@ __device__ __forceinline__ void q_sine_out3(QEpi& c, float s, const float4* __re
 // ------------------------------------------------------------------------------------------------------
 __constant__ QStep kQProgF[5] = {{0, 1}, {1, 1}, {2, 2}, {3, 2}, {4, 2}};
 using QSmemF = QSmem<5>;
-// consts: [0,256) unused  [256,320) 30 b1  [320,1344) float4 per hidden unit (30 b2, w3[0], w3[1], w3[2])  [1344,1347) b3
-//         [1348] s1 [1349] s2   [2048 + 256 nl, +256) e0 of timestamp nl: float4 (30 (b0 + w_t t), 30 w_rely, 30 w_relx, 0)
+// consts: [0,256) unused  [256,320) 30 b1  [320,1344) output weights per pair of hidden units (see q_sine_out3)  [1344,1347) b3
+//         [1348] s1 [1349] s2   [2048 + 256 nl, +256) e0 of timestamp nl, per pair of units (see q_table_layer0)
 // Work item = (timestamp of the group, reference frame, 128-pixel tile), timestamp-major.
 __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, float alpha, Scratch sc,
                                                                 float* __restrict__ flow_out) {
@@ -952,14 +996,21 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
   const int items_per_t = 2 * ((qs + 127) / 128);
   const int n_items = nt * items_per_t;
   const float* wp = sc.wpack;
-  for (int i = threadIdx.x; i < 64 * nt; i += blockDim.x) {
-    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 4 * (i & 63));
-    reinterpret_cast<float4*>(sm.consts + 2048)[i] = make_float4(fmaf(e.y, time_of(times, i >> 6), e.x) * kOmega, e.z * kOmega, e.w * kOmega, 0.f);
+  for (int i = threadIdx.x; i < 32 * nt; i += blockDim.x) {  // pair of units (2 pr, 2 pr + 1) of timestamp i / 32
+    const int pr = i & 31;
+    const float t = time_of(times, i >> 5);
+    const float4 e = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 8 * pr), f = *reinterpret_cast<const float4*>(wp + WeightPack::f_e0 + 8 * pr + 4);
+    float4* dst = reinterpret_cast<float4*>(sm.consts + 2048) + 2 * i;
+    dst[0] = make_float4(fmaf(e.y, t, e.x) * kOmega, fmaf(f.y, t, f.x) * kOmega, e.z * kOmega, f.z * kOmega);
+    dst[1] = make_float4(e.w * kOmega, f.w * kOmega, 0.f, 0.f);
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x) sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    reinterpret_cast<float4*>(sm.consts + 320)[i] =
-        make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 512 + i]);
+  for (int pr = threadIdx.x; pr < 128; pr += blockDim.x) {
+    const int i = 2 * pr;
+    float4* dst = reinterpret_cast<float4*>(sm.consts + 320) + 2 * pr;
+    dst[0] = make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_b2 + i + 1] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + i + 1]);
+    dst[1] = make_float4(wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 256 + i + 1], wp[WeightPack::f_a3 + 512 + i], wp[WeightPack::f_a3 + 512 + i + 1]);
+  }
   if (threadIdx.x < 3) sm.consts[1344 + threadIdx.x] = wp[WeightPack::f_b3 + threadIdx.x];
   if (threadIdx.x < 2) sm.consts[1348 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScF1 + threadIdx.x];
   q_setup(sm.bars);
@@ -1262,7 +1313,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
 __constant__ QStep kQProgS[6] = {{0, 1}, {1, 1}, {2, 1}, {3, 2}, {4, 2}, {5, 2}};
 using QSmemS = QSmem<6>;
 
-// consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) float4 per hidden unit (30 b3, w4[0], w4[1], w4[2])  [1152,1155) b4
+// consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) output weights per pair of hidden units (see q_sine_out3)  [1152,1155) b4
 //         [1156] s1  [1157] s2  [1158] s3
 // Work item = (timestamp of the group, 128 consecutive destinations in a-order), timestamp-major.
 __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, int items_per_t, Scratch sc,
@@ -1278,9 +1329,12 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
     sm.consts[i] = wp[WeightPack::s_b1 + i] * kOmega;
     sm.consts[64 + i] = wp[WeightPack::s_b2 + i] * kOmega;
   }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    reinterpret_cast<float4*>(sm.consts + 128)[i] =
-        make_float4(wp[WeightPack::s_b3 + i] * kOmega, wp[WeightPack::s_a4 + i], wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 512 + i]);
+  for (int pr = threadIdx.x; pr < 128; pr += blockDim.x) {
+    const int i = 2 * pr;
+    float4* dst = reinterpret_cast<float4*>(sm.consts + 128) + 2 * pr;
+    dst[0] = make_float4(wp[WeightPack::s_b3 + i] * kOmega, wp[WeightPack::s_b3 + i + 1] * kOmega, wp[WeightPack::s_a4 + i], wp[WeightPack::s_a4 + i + 1]);
+    dst[1] = make_float4(wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 256 + i + 1], wp[WeightPack::s_a4 + 512 + i], wp[WeightPack::s_a4 + 512 + i + 1]);
+  }
   if (threadIdx.x < 3) {
     sm.consts[1152 + threadIdx.x] = wp[WeightPack::s_b4 + threadIdx.x];
     sm.consts[1156 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScS1 + threadIdx.x];

@@ -1,7 +1,7 @@
 timeout 300 python -m pytest tests/test_decoder_gpu.py -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline > gpurun_out/s5_bench4.json 2> gpurun_out/s5_bench4.err; tail -3 gpurun_out/s5_bench4.err
-python -c "
-import json
-d=json.load(open('gpurun_out/s5_bench4.json'))
-print(d['ms_per_step'], d['e2e'])
-print({k: round(v['avg_ms'],3) for k,v in d['kernels'].items()})"
+run() { echo "== $*"; env "$@" python bench.py --no-cpu-baseline --steps 10 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print(round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), {k: round(v['avg_ms'],3) for k,v in d['kernels'].items()})"; }
+run MOTIF_ISSUER_MODE=1
+run MOTIF_ISSUER_MODE=0
