@@ -12,6 +12,8 @@
 //    Destinations with more than K contributions get the surplus through the atomic kernel below.
 //  * reference-order scatter with red.global.add.f32: the reference algorithm with the flow/weights
 //    hoisted out of the channel loop; used for the overflow and as an on-device cross-check.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace motif {
@@ -182,6 +184,36 @@ __device__ __forceinline__ void gather_channels(const float* __restrict__ plane,
   }
 }
 
+// Slots of one destination pixel: sorted by source index (Batcher odd-even merge network for 8 keys) so that the
+// accumulation order is source raster order whatever order the binning atomics handed the slots out in.
+template <int MODE>
+__device__ __forceinline__ int load_slots(const SplatWorkspace& ws, const float* __restrict__ metric, size_t total, size_t gd, int b, int hw,
+                                          bool live, unsigned (&src)[kBinSlots], float (&wt)[kBinSlots], float (&m)[kBinSlots]) {
+  const int cnt = live ? min(ws.count[gd], kBinSlots) : 0;
+  int srci[kBinSlots];
+#pragma unroll
+  for (int k = 0; k < kBinSlots; ++k) {
+    const bool on = k < cnt;
+    srci[k] = on ? ws.ent_src[(size_t)k * total + gd] : 0x7fffffff;
+    wt[k] = on ? ws.ent_w[(size_t)k * total + gd] : 0.0f;
+  }
+#define CS(a, b) cswap(srci[a], wt[a], srci[b], wt[b])
+  CS(0, 1); CS(2, 3); CS(4, 5); CS(6, 7);
+  CS(0, 2); CS(1, 3); CS(4, 6); CS(5, 7);
+  CS(1, 2); CS(5, 6);
+  CS(0, 4); CS(1, 5); CS(2, 6); CS(3, 7);
+  CS(2, 4); CS(3, 5);
+  CS(1, 2); CS(3, 4); CS(5, 6);
+#undef CS
+#pragma unroll
+  for (int k = 0; k < kBinSlots; ++k) {
+    src[k] = (k < cnt) ? (unsigned)srci[k] : 0u;
+    m[k] = 1.0f;
+    if (MODE >= MOTIF_SPLAT_LINEAR && k < cnt) m[k] = metric_scale<MODE>(metric, (size_t)b * hw + src[k]);
+  }
+  return cnt;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restrict__ in, const float* __restrict__ metric,
                                                            float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
@@ -192,39 +224,187 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restri
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = d < hw;
   const size_t gd = (size_t)b * hw + (live ? d : 0);
-  const int cnt = live ? min(ws.count[gd], kBinSlots) : 0;
-  int srci[kBinSlots];
-  float wt[kBinSlots];
-#pragma unroll
-  for (int k = 0; k < kBinSlots; ++k) {
-    const bool on = k < cnt;
-    srci[k] = on ? ws.ent_src[(size_t)k * total + gd] : 0x7fffffff;
-    wt[k] = on ? ws.ent_w[(size_t)k * total + gd] : 0.0f;
-  }
-  // sort by source index (Batcher odd-even merge network for 8 keys): the accumulation order becomes
-  // source raster order whatever order the binning atomics handed the slots out in.
-#define CS(a, b) cswap(srci[a], wt[a], srci[b], wt[b])
-  CS(0, 1); CS(2, 3); CS(4, 5); CS(6, 7);
-  CS(0, 2); CS(1, 3); CS(4, 6); CS(5, 7);
-  CS(1, 2); CS(5, 6);
-  CS(0, 4); CS(1, 5); CS(2, 6); CS(3, 7);
-  CS(2, 4); CS(3, 5);
-  CS(1, 2); CS(3, 4); CS(5, 6);
-#undef CS
   unsigned src[kBinSlots];
-  float m[kBinSlots];
-#pragma unroll
-  for (int k = 0; k < kBinSlots; ++k) {
-    src[k] = (k < cnt) ? (unsigned)srci[k] : 0u;
-    m[k] = 1.0f;
-    if (MODE >= MOTIF_SPLAT_LINEAR && k < cnt) m[k] = metric_scale<MODE>(metric, (size_t)b * hw + src[k]);
-  }
+  float wt[kBinSlots], m[kBinSlots];
+  const int cnt = load_slots<MODE>(ws, metric, total, gd, b, hw, live, src, wt, m);
   const int wmax = __reduce_max_sync(0xffffffffu, cnt);
   const float* plane = in + (size_t)b * c * hw;
   float* optr = out + (size_t)b * c_out * hw + (live ? d : 0);
   if (wmax <= 4) gather_channels<MODE, 4>(plane, optr, c, hw, cnt, src, wt, m, live);
   else if (wmax <= 6) gather_channels<MODE, 6>(plane, optr, c, hw, cnt, src, wt, m, live);
   else gather_channels<MODE, 8>(plane, optr, c, hw, cnt, src, wt, m, live);
+  if (MODE != MOTIF_SPLAT_SUMMATION && live) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kBinSlots; ++k)
+      if (k < cnt) acc = __fadd_rn(acc, __fmul_rn(m[k], wt[k]));
+    optr[(size_t)c * hw] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Destination-centric pass 2, tiled: one CTA = a 32 x 8 tile of destination pixels, one thread per destination.
+// The sources a tile gathers from lie in a small window of every channel plane (the tile moved by the local flow,
+// plus its spread); the window of kCH channels at a time is staged into shared memory with 16-byte cp.async copies
+// (each input element crosses L2 -> SM once per tile instead of once per destination that uses it -- four on
+// average -- and as full sectors instead of 4-byte gathers), double-buffered against the accumulation, which
+// then gathers with LDS and runs two channels per instruction (FMUL2 / FADD2; each lane rounds like the scalar
+// op, order unchanged: still bit-exact against the reference kernel in raster order).  Tiles whose window does
+// not fit (strongly diverging flow) and planes whose rows are not 16-byte aligned take the direct path above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTW = 32, kTH = 8;    // destination tile
+constexpr int kRW = 64, kRH = 16;   // staged source window (floats x rows): 16 x 16 16-byte columns, one per thread
+constexpr int kPlane = kRH * kRW + 4; // floats per staged channel plane: the window + a zero word (16-byte padded)
+constexpr int kStages = 3;          // staged chunks in flight (prefetch distance kStages - 1)
+constexpr int kTiledSmem = kStages * 8 * kPlane * (int)sizeof(float);
+constexpr int kCH = 8;              // channels per stage
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// channels [0, nch) of one staged chunk, K slots per destination, two channels per instruction.  Slots past the
+// list length point at the zero word that follows every staged plane and carry weight 0: they add +0 (exact) without a
+// predicate, and can never pick up a non-finite input the way a real window element could.
+template <int MODE, int K, bool FULL>
+__device__ __forceinline__ void tile_channels(const float* __restrict__ stage, float* __restrict__ optr, int nch, size_t hw,
+                                              const int (&off)[kBinSlots], const float (&wt)[kBinSlots], const float (&m)[kBinSlots], bool store) {
+#pragma unroll
+  for (int cp = 0; cp < kCH / 2; ++cp) {
+    if (!FULL && 2 * cp >= nch) break;
+    const float* p0 = stage + (2 * cp) * kPlane;
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      f32x2 t = pack2(p0[off[k]], p0[off[k] + kPlane]);
+      if (MODE >= MOTIF_SPLAT_LINEAR) t = fmul2(t, pack2(m[k], m[k]));
+      t = fmul2(t, pack2(wt[k], wt[k]));
+      // scalar adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding instead of the reference's two)
+      float t0, t1;
+      unpack2(t, t0, t1);
+      a0 = __fadd_rn(a0, t0);
+      a1 = __fadd_rn(a1, t1);
+    }
+    if (store) {
+      optr[0] = a0;
+      if (FULL || 2 * cp + 1 < nch) optr[hw] = a1;
+    }
+    optr += 2 * hw;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) splat_gather_tiled_kernel(const float* __restrict__ in, const float* __restrict__ metric,
+                                                                 float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
+  extern __shared__ __align__(16) float buf_raw[];  // [kStages][kCH][kPlane]
+  float(*buf)[kCH * kPlane] = reinterpret_cast<float(*)[kCH * kPlane]>(buf_raw);
+  if (threadIdx.x < kStages * kCH) buf_raw[threadIdx.x * kPlane + kRH * kRW] = 0.0f;  // the zero word of every plane
+  __shared__ int s_box[4];  // min x, min y, max x, max y of the sources this tile gathers from
+  const int hw = h * w;
+  const size_t total = (size_t)n * hw;
+  const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
+  const int b = blockIdx.y;
+  const int tiles_x = (w + kTW - 1) / kTW;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = ((int)blockIdx.x % tiles_x) * kTW + tx, y = ((int)blockIdx.x / tiles_x) * kTH + ty;
+  const bool live = (x < w) & (y < h);
+  const int d = live ? y * w + x : 0;
+  const size_t gd = (size_t)b * hw + d;
+  if (threadIdx.x == 0) s_box[0] = s_box[1] = 0x7fffffff, s_box[2] = s_box[3] = -1;
+  unsigned src[kBinSlots];
+  float wt[kBinSlots], m[kBinSlots];
+  const int cnt = load_slots<MODE>(ws, metric, total, gd, b, hw, live, src, wt, m);
+  int sx[kBinSlots], sy[kBinSlots];
+  int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = -1, mxy = -1;
+#pragma unroll
+  for (int k = 0; k < kBinSlots; ++k) {
+    sy[k] = (int)(src[k] / (unsigned)w);
+    sx[k] = (int)(src[k] - (unsigned)sy[k] * (unsigned)w);
+    if (k < cnt) mnx = min(mnx, sx[k]), mny = min(mny, sy[k]), mxx = max(mxx, sx[k]), mxy = max(mxy, sy[k]);
+  }
+  mnx = __reduce_min_sync(0xffffffffu, mnx), mny = __reduce_min_sync(0xffffffffu, mny);
+  mxx = __reduce_max_sync(0xffffffffu, mxx), mxy = __reduce_max_sync(0xffffffffu, mxy);
+  const int wmax = __reduce_max_sync(0xffffffffu, cnt);
+  __syncthreads();
+  if (tx == 0 && mxx >= 0) atomicMin(&s_box[0], mnx), atomicMin(&s_box[1], mny), atomicMax(&s_box[2], mxx), atomicMax(&s_box[3], mxy);
+  __syncthreads();
+  const int x0a = s_box[0] & ~3, y0 = s_box[1];
+  const int rw4 = (((s_box[2] + 4) & ~3) - x0a) >> 2, rh = s_box[3] - y0 + 1;  // window: rw4 16-byte columns x rh rows
+  const float* plane = in + (size_t)b * c * hw;
+  float* optr = out + (size_t)b * c_out * hw + d;
+  const bool empty = s_box[2] < 0;
+  if (!empty && (rw4 * 4 > kRW || rh > kRH)) {  // window too large for the stage: direct gathers (block-uniform branch)
+    if (wmax <= 4) gather_channels<MODE, 4>(plane, optr, c, hw, cnt, src, wt, m, live);
+    else if (wmax <= 6) gather_channels<MODE, 6>(plane, optr, c, hw, cnt, src, wt, m, live);
+    else gather_channels<MODE, 8>(plane, optr, c, hw, cnt, src, wt, m, live);
+  } else {
+    int off[kBinSlots];
+#pragma unroll
+    for (int k = 0; k < kBinSlots; ++k) {
+      const bool on = k < cnt;
+      off[k] = on ? (sy[k] - y0) * kRW + (sx[k] - x0a) : kRH * kRW;
+      wt[k] = on ? wt[k] : 0.0f;
+      m[k] = on ? m[k] : 1.0f;
+    }
+    // this thread's 16-byte column of the window (same for every channel)
+    const int n16 = empty ? 0 : rw4 * rh;
+    const bool copier = (int)threadIdx.x < n16;
+    const int crow = copier ? (int)threadIdx.x / rw4 : 0, ccol = copier ? (int)threadIdx.x - crow * rw4 : 0;
+    const float* csrc = plane + (size_t)(y0 + crow) * w + x0a + 4 * ccol;
+    const int cdst = crow * kRW + 4 * ccol;
+    const int n_chunks = (c + kCH - 1) / kCH;
+    auto stage_in = [&](int q) {
+      if (copier) {
+        const int c0 = q * kCH, nch = min(kCH, c - c0);
+        float* dst = &buf[q % kStages][cdst];
+        const float* sp = csrc + (size_t)c0 * hw;
+        for (int ch = 0; ch < nch; ++ch) cp_async16(dst + ch * kPlane, sp + (size_t)ch * hw);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int q = 0; q < kStages - 1; ++q) {
+      if (q < n_chunks) stage_in(q);
+      else cp_async_commit();
+    }
+    for (int q = 0; q < n_chunks; ++q) {
+      if (q + kStages - 1 < n_chunks) stage_in(q + kStages - 1);  // refills the stage read in iteration q - 1 (barrier below)
+      else cp_async_commit();
+      cp_async_wait<kStages - 1>();
+      __syncthreads();
+      const int c0 = q * kCH, nch = min(kCH, c - c0);
+      float* o = optr + (size_t)c0 * hw;
+      const float* st = buf[q % kStages];
+      if (nch == kCH) {
+        if (wmax <= 4) tile_channels<MODE, 4, true>(st, o, nch, hw, off, wt, m, live);
+        else if (wmax <= 6) tile_channels<MODE, 6, true>(st, o, nch, hw, off, wt, m, live);
+        else tile_channels<MODE, 8, true>(st, o, nch, hw, off, wt, m, live);
+      } else {
+        tile_channels<MODE, 8, false>(st, o, nch, hw, off, wt, m, live);
+      }
+      __syncthreads();  // this stage is refilled by the next iteration's stage_in
+    }
+  }
   if (MODE != MOTIF_SPLAT_SUMMATION && live) {
     float acc = 0.0f;
 #pragma unroll
@@ -300,12 +480,23 @@ static int launch_scatter(const float* in, const float* flow, const float* metri
 template <int MODE>
 static int launch_gather(const float* in, const float* metric, float* out, const SplatWorkspace& ws, int n, int c, int h, int w,
                          cudaStream_t st) {
-  dim3 grid(ceil_div((long long)h * w, 256), n);
-  {
-    ProfScope prof("splat_gather_kernel", st);
+  // the tiled kernel stages 16-byte columns: every plane row must start 16-byte aligned
+  static const bool force_direct = getenv("MOTIF_SPLAT_DIRECT") != nullptr;
+  const bool tiled = !force_direct && (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  ProfScope prof("splat_gather_kernel", st);
+  if (tiled) {
+    dim3 grid(ceil_div(w, kTW) * ceil_div(h, kTH), n);
+    static bool attr_done = false;  // per MODE instantiation
+    if (!attr_done) {
+      MOTIF_CUDA(cudaFuncSetAttribute(splat_gather_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem));
+      attr_done = true;
+    }
+    splat_gather_tiled_kernel<MODE><<<grid, 256, kTiledSmem, st>>>(in, metric, out, ws, n, c, h, w);
+  } else {
+    dim3 grid(ceil_div((long long)h * w, 256), n);
     splat_gather_kernel<MODE><<<grid, 256, 0, st>>>(in, metric, out, ws, n, c, h, w);
-    MOTIF_LAUNCHED("splat_gather_kernel");
   }
+  MOTIF_LAUNCHED("splat_gather_kernel");
   return 0;
 }
 
