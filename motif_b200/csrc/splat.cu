@@ -25,7 +25,8 @@ struct SplatWorkspace {
   int* ent_src;    // [K][n*hw] source pixel (y*w+x) of slot k
   float* ent_w;    // [K][n*hw] bilinear weight of slot k
   unsigned char* ovf_mask;  // [n*hw] per SOURCE pixel: bit c set = corner c did not get a slot
-  int* ovf_total;  // [1]
+  int* ovf_total;  // [1]   number of source pixels with a non-zero mask
+  int* ovf_list;   // [n*hw] those source pixels (global index b*hw + s), in no particular order
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -43,7 +44,9 @@ static size_t workspace_layout(int n, int h, int w, SplatWorkspace* ws, char* ba
   char* c = take(p * sizeof(float) * kBinSlots);
   char* d = take(p);
   char* e = take(256);
+  char* f = take(p * sizeof(int));
   if (ws) {
+    ws->ovf_list = (int*)f;
     ws->count = (int*)a;
     ws->ent_src = (int*)b;
     ws->ent_w = (float*)c;
@@ -52,6 +55,9 @@ static size_t workspace_layout(int n, int h, int w, SplatWorkspace* ws, char* ba
   }
   return off;
 }
+
+// more than 1/64 of the source pixels overflowed a destination list
+__host__ __device__ inline bool surplus_is_dense(int n_list, long long n_src) { return (long long)n_list * 64 > n_src; }
 
 template <int MODE>
 __device__ __forceinline__ float metric_scale(const float* metric, size_t idx) {
@@ -70,8 +76,10 @@ __global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restr
                                                             int n, int c, int h, int w,
                                                             const unsigned char* __restrict__ ovf_mask,
                                                             const int* __restrict__ ovf_total) {
-  if (ovf_total != nullptr && *ovf_total == 0) return;
   const int hw = h * w;
+  // surplus pass: this (thread per source, neighbouring sources coalesce) kernel takes the dense regime, the
+  // warp-per-listed-source kernel the sparse one; both are launched and one of them returns at once
+  if (ovf_total != nullptr && !surplus_is_dense(*ovf_total, (long long)n * hw)) return;
   const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)n * hw;
        p += (long long)gridDim.x * blockDim.x) {
@@ -112,6 +120,49 @@ __global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restr
   }
 }
 
+// Surplus of the binning pass: one WARP per listed source pixel, lanes over channels (the list is sparse, so a thread
+// per source would leave most of a warp idle and serialise 130 channels of atomics behind one thread).
+template <int MODE>
+__global__ void __launch_bounds__(256) splat_scatter_list_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                                 const float* __restrict__ metric, float* __restrict__ out,
+                                                                 int n, int c, int h, int w, SplatWorkspace ws) {
+  const int hw = h * w;
+  const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
+  const int n_list = *ws.ovf_total;
+  if (surplus_is_dense(n_list, (long long)n * hw)) return;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_list; i += warps) {
+    const int p = ws.ovf_list[i];
+    const unsigned mask = ws.ovf_mask[p];
+    const int b = p / hw, s = p - b * hw;
+    const int y = s / w, x = s - y * w;
+    const Footprint f = footprint(x, y, flow[((size_t)b * 2 + 0) * hw + s], flow[((size_t)b * 2 + 1) * hw + s]);
+    if (!f.finite) continue;
+    int dst[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int cx, cy;
+      ok[k] = corner_inside(f, k, w, h, cx, cy) && ((mask >> k) & 1);
+      dst[k] = cy * w + cx;
+    }
+    const float m = metric_scale<MODE>(metric, p);
+    const float* src = in + (size_t)b * c * hw + s;
+    float* o = out + (size_t)b * c_out * hw;
+    for (int ch = lane; ch < c_out; ch += 32) {
+      float v = m;  // the normaliser channel (ch == c) splats the metric scale itself
+      if (ch < c) {
+        v = src[(size_t)ch * hw];
+        if (MODE >= MOTIF_SPLAT_LINEAR) v = __fmul_rn(v, m);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) red_add_f32(o + (size_t)ch * hw + dst[k], __fmul_rn(v, f.w[k]));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Destination-centric pass 1: bin (source, weight) per destination pixel.
 // ------------------------------------------------------------------------------------------------
@@ -140,7 +191,7 @@ __global__ void __launch_bounds__(256) splat_bin_kernel(const float* __restrict_
     }
     if (overflow) {
       ws.ovf_mask[p] = (unsigned char)overflow;
-      atomicAdd(ws.ovf_total, 1);
+      ws.ovf_list[atomicAdd(ws.ovf_total, 1)] = (int)p;
     }
   }
 }
@@ -189,13 +240,20 @@ __device__ __forceinline__ void gather_channels(const float* __restrict__ plane,
 template <int MODE>
 __device__ __forceinline__ int load_slots(const SplatWorkspace& ws, const float* __restrict__ metric, size_t total, size_t gd, int b, int hw,
                                           bool live, unsigned (&src)[kBinSlots], float (&wt)[kBinSlots], float (&m)[kBinSlots]) {
-  const int cnt = live ? min(ws.count[gd], kBinSlots) : 0;
+  // every slot is read in the same round trip as the count (slots past the count hold stale values: masked below)
+  const int cnt_raw = ws.count[gd];
   int srci[kBinSlots];
 #pragma unroll
   for (int k = 0; k < kBinSlots; ++k) {
+    srci[k] = ws.ent_src[(size_t)k * total + gd];
+    wt[k] = ws.ent_w[(size_t)k * total + gd];
+  }
+  const int cnt = live ? min(cnt_raw, kBinSlots) : 0;
+#pragma unroll
+  for (int k = 0; k < kBinSlots; ++k) {
     const bool on = k < cnt;
-    srci[k] = on ? ws.ent_src[(size_t)k * total + gd] : 0x7fffffff;
-    wt[k] = on ? ws.ent_w[(size_t)k * total + gd] : 0.0f;
+    srci[k] = on ? srci[k] : 0x7fffffff;
+    wt[k] = on ? wt[k] : 0.0f;
   }
 #define CS(a, b) cswap(srci[a], wt[a], srci[b], wt[b])
   CS(0, 1); CS(2, 3); CS(4, 5); CS(6, 7);
@@ -255,7 +313,7 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restri
 constexpr int kTW = 32, kTH = 8;    // destination tile
 constexpr int kRW = 64, kRH = 16;   // staged source window (floats x rows): 16 x 16 16-byte columns, one per thread
 constexpr int kPlane = kRH * kRW + 4; // floats per staged channel plane: the window + a zero word (16-byte padded)
-constexpr int kStages = 3;          // staged chunks in flight (prefetch distance kStages - 1)
+constexpr int kStages = 3;          // staged chunks: one being read, kStages - 1 in flight (>= 3: one barrier per chunk suffices)
 constexpr int kTiledSmem = kStages * 8 * kPlane * (int)sizeof(float);
 constexpr int kCH = 8;              // channels per stage
 
@@ -388,10 +446,10 @@ __global__ void __launch_bounds__(256) splat_gather_tiled_kernel(const float* __
       else cp_async_commit();
     }
     for (int q = 0; q < n_chunks; ++q) {
-      if (q + kStages - 1 < n_chunks) stage_in(q + kStages - 1);  // refills the stage read in iteration q - 1 (barrier below)
+      cp_async_wait<kStages - 2>();  // chunk q has landed (this thread's copies; the barrier publishes everyone's)
+      __syncthreads();               // ... and every thread is done with chunk q - 1, whose stage is refilled next
+      if (q + kStages - 1 < n_chunks) stage_in(q + kStages - 1);
       else cp_async_commit();
-      cp_async_wait<kStages - 1>();
-      __syncthreads();
       const int c0 = q * kCH, nch = min(kCH, c - c0);
       float* o = optr + (size_t)c0 * hw;
       const float* st = buf[q % kStages];
@@ -402,7 +460,6 @@ __global__ void __launch_bounds__(256) splat_gather_tiled_kernel(const float* __
       } else {
         tile_channels<MODE, 8, false>(st, o, nch, hw, off, wt, m, live);
       }
-      __syncthreads();  // this stage is refilled by the next iteration's stage_in
     }
   }
   if (MODE != MOTIF_SPLAT_SUMMATION && live) {
@@ -474,6 +531,17 @@ static int launch_scatter(const float* in, const float* flow, const float* metri
     splat_scatter_kernel<MODE><<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, metric, out, n, c, h, w, mask, total);
     MOTIF_LAUNCHED("splat_scatter_kernel");
   }
+  return 0;
+}
+
+template <int MODE>
+static int launch_surplus(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w, const SplatWorkspace& ws,
+                          cudaStream_t st) {
+  ProfScope prof("splat_scatter_kernel", st);
+  splat_scatter_list_kernel<MODE><<<148 * 4, 256, 0, st>>>(in, flow, metric, out, n, c, h, w, ws);
+  MOTIF_LAUNCHED("splat_scatter_kernel");
+  splat_scatter_kernel<MODE><<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total);
+  MOTIF_LAUNCHED("splat_scatter_kernel");
   return 0;
 }
 
@@ -555,19 +623,19 @@ extern "C" int motif_splat_fwd(const float* in, const float* flow, const float* 
   switch (mode) {
     case MOTIF_SPLAT_SUMMATION:
       rc = launch_gather<MOTIF_SPLAT_SUMMATION>(in, metric, out, ws, n, c, h, w, st);
-      if (!rc) rc = launch_scatter<MOTIF_SPLAT_SUMMATION>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      if (!rc) rc = launch_surplus<MOTIF_SPLAT_SUMMATION>(in, flow, metric, out, n, c, h, w, ws, st);
       break;
     case MOTIF_SPLAT_AVERAGE:
       rc = launch_gather<MOTIF_SPLAT_AVERAGE>(in, metric, out, ws, n, c, h, w, st);
-      if (!rc) rc = launch_scatter<MOTIF_SPLAT_AVERAGE>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      if (!rc) rc = launch_surplus<MOTIF_SPLAT_AVERAGE>(in, flow, metric, out, n, c, h, w, ws, st);
       break;
     case MOTIF_SPLAT_LINEAR:
       rc = launch_gather<MOTIF_SPLAT_LINEAR>(in, metric, out, ws, n, c, h, w, st);
-      if (!rc) rc = launch_scatter<MOTIF_SPLAT_LINEAR>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      if (!rc) rc = launch_surplus<MOTIF_SPLAT_LINEAR>(in, flow, metric, out, n, c, h, w, ws, st);
       break;
     default:
       rc = launch_gather<MOTIF_SPLAT_SOFTMAX>(in, metric, out, ws, n, c, h, w, st);
-      if (!rc) rc = launch_scatter<MOTIF_SPLAT_SOFTMAX>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total, st);
+      if (!rc) rc = launch_surplus<MOTIF_SPLAT_SOFTMAX>(in, flow, metric, out, n, c, h, w, ws, st);
       break;
   }
   return rc;
