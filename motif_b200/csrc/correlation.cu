@@ -7,6 +7,13 @@
 // straight from NCHW into shared memory (zero padding applied while staging, no rearranged copies), and
 // each thread keeps a 4-pixel x 9-dx x 3-dy register tile (108 accumulators) fed by float4 shared loads,
 // so every staged value is reused 81 times from registers/shared memory.
+//
+// The coarse PWC-Net levels are tiny images with many channels (196 x 12 x 20: two tiles), far too few CTAs for 148
+// SMs.  There the channel range is split over a thread-block CLUSTER (up to 8 CTAs per output tile): every CTA
+// accumulates its slice, the partial register tiles are parked in shared memory and the cluster's rank 0 adds them in
+// rank order through distributed shared memory -- deterministic, no atomics, no workspace, output written once.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace motif {
@@ -18,12 +25,19 @@ constexpr int kWinW = kTX + 8;
 constexpr int kWinH = kTY + 8;
 constexpr int kCorrThreads = 8 * kTY * 3;  // 8 x-groups of 4 pixels, kTY rows, 3 dy-groups of 3
 
+constexpr int kAccPerThread = 3 * 9 * 4;
+constexpr int kCorrPartBytes = kAccPerThread * kCorrThreads * (int)sizeof(float);  // parked partial tile of one CTA
+
+// grid.z = batch * ksplit; the ksplit CTAs of one output tile form a cluster (1, 1, ksplit)
 __global__ void __launch_bounds__(kCorrThreads) corr_kernel(const float* __restrict__ first, const float* __restrict__ second,
-                                                            float* __restrict__ out, int c, int h, int w) {
+                                                            float* __restrict__ out, int c, int h, int w, int ksplit) {
   __shared__ __align__(16) float s1[kCC][kTY][kTX];
   __shared__ __align__(16) float s2[kCC][kWinH][kWinW];
+  extern __shared__ __align__(16) float part[];  // [kAccPerThread][kCorrThreads] when ksplit > 1
 
-  const int b = blockIdx.z;
+  const int b = blockIdx.z / ksplit, krank = blockIdx.z % ksplit;
+  const int n_chunks = (c + kCC - 1) / kCC;
+  const int chunk0 = (int)((long long)n_chunks * krank / ksplit), chunk1 = (int)((long long)n_chunks * (krank + 1) / ksplit);
   const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
   const int tid = threadIdx.x;
   const int xg = tid & 7;          // which 4-pixel group
@@ -41,7 +55,7 @@ __global__ void __launch_bounds__(kCorrThreads) corr_kernel(const float* __restr
 #pragma unroll
       for (int p = 0; p < 4; ++p) acc[r][d][p] = 0.0f;
 
-  for (int c0 = 0; c0 < c; c0 += kCC) {
+  for (int c0 = chunk0 * kCC; c0 < chunk1 * kCC; c0 += kCC) {
     const int cc = min(kCC, c - c0);
     __syncthreads();
     for (int i = tid; i < kCC * kTY * kTX; i += kCorrThreads) {
@@ -78,6 +92,32 @@ __global__ void __launch_bounds__(kCorrThreads) corr_kernel(const float* __restr
     }
   }
 
+  if (ksplit > 1) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    if (krank != 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int d = 0; d < 9; ++d)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) part[((r * 9 + d) * 4 + p) * kCorrThreads + tid] = acc[r][d][p];
+    }
+    cluster.sync();
+    if (krank == 0) {
+      for (int k = 1; k < ksplit; ++k) {
+        const float* remote = cluster.map_shared_rank(part, k);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int d = 0; d < 9; ++d)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[r][d][p] += remote[((r * 9 + d) * 4 + p) * kCorrThreads + tid];
+      }
+    }
+    cluster.sync();  // the parked tiles stay alive until rank 0 has read them
+    if (krank != 0) return;
+  }
   const int y = y0 + ty;
   if (y >= h) return;
   const float denom = (float)c;
@@ -101,11 +141,31 @@ using namespace motif;
 extern "C" int motif_corr_fwd(const float* first, const float* second, float* out, int b, int c, int h, int w, void* stream) {
   MOTIF_REQUIRE(first && second && out, "corr: null pointer");
   MOTIF_REQUIRE(b > 0 && c > 0 && h > 0 && w > 0, "corr: non-positive size b=%d c=%d h=%d w=%d", b, c, h, w);
-  MOTIF_REQUIRE(b <= 65535, "corr: batch too large");
-  dim3 grid(ceil_div(w, kTX), ceil_div(h, kTY), b);
+  const int tiles = ceil_div(w, kTX) * ceil_div(h, kTY) * b;
+  // split the channels over a cluster while the grid would leave most of the 148 SMs idle (2 CTAs fit per SM)
+  int ksplit = 1;
+  while (ksplit < 8 && tiles * ksplit * 2 <= 296 && ceil_div(c, kCC) >= ksplit * 4) ksplit *= 2;
+  MOTIF_REQUIRE((long long)b * ksplit <= 65535, "corr: batch too large");
+  static bool attr_done = false;
+  if (!attr_done) {
+    MOTIF_CUDA(cudaFuncSetAttribute(corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrPartBytes));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(w, kTX), ceil_div(h, kTY), b * ksplit);
+  cfg.blockDim = dim3(kCorrThreads);
+  cfg.dynamicSmemBytes = ksplit > 1 ? kCorrPartBytes : 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = ksplit;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   {
     ProfScope prof("corr_kernel", (cudaStream_t)stream);
-    corr_kernel<<<grid, kCorrThreads, 0, (cudaStream_t)stream>>>(first, second, out, c, h, w);
+    MOTIF_CUDA(cudaLaunchKernelEx(&cfg, corr_kernel, first, second, out, c, h, w, ksplit));
     MOTIF_LAUNCHED("corr_kernel");
   }
   return 0;
