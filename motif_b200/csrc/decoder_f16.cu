@@ -1035,77 +1035,88 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
     const float s1 = sm.consts[1348], s2 = sm.consts[1349];
     const int row = c.quad * 32 + lane;
     const int n_iters = q_iters(n_items, c.tile);
-    for (int it = 0; it < n_iters; ++it) {
-      TRACE_Q(c, 1);
-      const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
+    // The three splats of item i are issued AFTER the first-layer operand of item i + 1 has been published: their atomics
+    // (a return-value round trip through L2 before the dependent list store) then overlap that item's first MMA instead
+    // of holding the tile's four warps back from it.
+    float p_dx = 0.f, p_dy = 0.f, p_z = 0.f;
+    int p_item = -1;
+    auto scatter = [&](int item, float dx, float dy, float zraw) {
       const int nl = item / items_per_t, rem = item - nl * items_per_t;
       const int n = n0 + nl;
-      const float4* e0 = reinterpret_cast<const float4*>(sm.consts + 2048 + 256 * nl);
-      const int r = rem & 1;
-      const int rb = r * B + b;
+      const int rb = (rem & 1) * B + b;
       const int q = (rem >> 1) * 128 + row;
-      const bool live = q < qs;
-      const int qc = live ? q : qs - 1;
-      const int qy = qc / g.WW, qx = qc % g.WW;
-      const Query qu = make_query(qy, qx, g);
-      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
-      q_table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
-      q_sine_epilogue(c, s1, sm.consts + 256);
-      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
-      TRACE_Q(c, 2);
-
+      if (q >= qs) return;
+      const int qy = q / g.WW, qx = q - qy * g.WW;
       // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
       const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
       const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
       const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
       const float e = expf(z);
-      if (live && flow_out != nullptr) {
+      if (flow_out != nullptr) {
         float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
         fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
         fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
       }
       const Footprint f = footprint(qx, qy, fx, fy);
-      if (live && f.finite) {
-        const uint32_t id = (uint32_t)((size_t)rb * qs + q);
-        const size_t dbase = ((size_t)nl * B + b) * qs;  // this timestamp's destination arrays
-        const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
-        int slot[4];
-        size_t dd[4];
-        bool ok[4];
-        // all four slot requests go out before any of them is consumed
+      if (!f.finite) return;
+      const uint32_t id = (uint32_t)((size_t)rb * qs + q);
+      const size_t dbase = ((size_t)nl * B + b) * qs;  // this timestamp's destination arrays
+      const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
+      int slot[4];
+      size_t dd[4];
+      bool ok[4];
+      // all four slot requests go out before any of them is consumed
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
-          ok[k] = !((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH));
-          dd[k] = dbase + (size_t)(ok[k] ? cy : 0) * g.WW + (ok[k] ? cx : 0);
-          slot[k] = ok[k] ? atomicAdd(sc.bin_count + dd[k], 1) : 0;
-        }
+      for (int k = 0; k < 4; ++k) {
+        const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
+        ok[k] = !((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH));
+        dd[k] = dbase + (size_t)(ok[k] ? cy : 0) * g.WW + (ok[k] ? cx : 0);
+        slot[k] = ok[k] ? atomicAdd(sc.bin_count + dd[k], 1) : 0;
+      }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (!ok[k]) continue;
-          const size_t d = dd[k];
-          const float wk = f.w[k];
-          const float we = __fmul_rn(e, wk);
-          red_add_v4(sc.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
-          // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
-          if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
-          if (slot[k] < kSlots) {
-            sc.bin_ent[d * kSlots + slot[k]] = make_uint2(id, __float_as_uint(we));
-          } else {
-            const float4* y4 = reinterpret_cast<const float4*>(sc.Y + (size_t)id * 64);
-            float* sp = sc.spill + d * 64;
+      for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        const size_t d = dd[k];
+        const float wk = f.w[k];
+        const float we = __fmul_rn(e, wk);
+        red_add_v4(sc.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
+        // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
+        if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
+        if (slot[k] < kSlots) {
+          sc.bin_ent[d * kSlots + slot[k]] = make_uint2(id, __float_as_uint(we));
+        } else {
+          const float4* y4 = reinterpret_cast<const float4*>(sc.Y + (size_t)id * 64);
+          float* sp = sc.spill + d * 64;
 #pragma unroll 4
-            for (int j4 = 0; j4 < 16; ++j4) {
-              const float4 y = __ldg(y4 + j4);
-              red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
-            }
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 y = __ldg(y4 + j4);
+            red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
           }
         }
       }
+    };
+    for (int it = 0; it < n_iters; ++it) {
+      TRACE_Q(c, 1);
+      const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
+      const int nl = item / items_per_t, rem = item - nl * items_per_t;
+      const float4* e0 = reinterpret_cast<const float4*>(sm.consts + 2048 + 256 * nl);
+      const int rb = (rem & 1) * B + b;
+      const int q = (rem >> 1) * 128 + row;
+      const int qc = q < qs ? q : qs - 1;
+      const int qy = qc / g.WW, qx = qc % g.WW;
+      const Query qu = make_query(qy, qx, g);
+      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
+      q_table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
+      if (p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
       TRACE_Q(c, 4);
+      q_sine_epilogue(c, s1, sm.consts + 256);
+      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
+      TRACE_Q(c, 2);
+      p_dx = dx, p_dy = dy, p_z = zraw, p_item = item;
     }
+    if (p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
   }
   teardown(0);
 }

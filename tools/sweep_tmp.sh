@@ -1,6 +1,6 @@
-timeout 600 python -m pytest tests/test_splat_gpu.py -m gpu -x -q 2>&1 | tail -2
-python tools/bench_splat.py 2>&1 | tail -8
-python bench.py --no-cpu-baseline --steps 5 2>/dev/null | python -c "
+timeout 300 python -m pytest tests/test_decoder_gpu.py -m gpu -x -q 2>&1 | tail -3
+run() { echo "== $*"; env "$@" python bench.py --no-cpu-baseline --steps 10 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print(d['roofline_splat'])"
+print(round(d['ms_per_step'],3), round(d['e2e']['ms_per_step'],3), {k: round(v['avg_ms'],3) for k,v in d['kernels'].items()})"; }
+run A=1
