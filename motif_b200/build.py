@@ -52,6 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-c", src, "-o", obj]
         if os.environ.get("MOTIF_TRACE"):
             cmd.insert(1, "-DMOTIF_TRACE")
+        for d in os.environ.get("MOTIF_DEFINES", "").split():  # tuning switches, e.g. MOTIF_DEFINES="MOTIF_OUT3_CONST"
+            cmd.insert(1, "-D" + d)
         if verbose:
             cmd += ["-Xptxas", "-v"]
             print(" ".join(cmd))

@@ -109,6 +109,7 @@ struct Scratch {
   float* fold;              // [64][256] W0a*W3 then [64] W0a*b3
   float* scales;            // [kNumSc] power-of-two weight scales, then [kNumSc] their inverses
   unsigned char* wimg;      // [kNumImg] fp16 block images
+  float* out3c;             // [2][1024] staging of the output-layer constants (flow_imnet, synth_net) for the constant bank
   float* p0f;               // [2B][P][64]  30 * W0f[:, :64] * flow_feat
   float* p0i;               // [2B][P][64]  30 * W0i[:, :64] * feat
   float* ftab;              // [2B][P][64]  30 * W0b * feat
@@ -138,6 +139,7 @@ static int layout(int B, int NT, int H, int W, int HH, int WW, Scratch* s, char*
   t.fold = (float*)take(sizeof(float) * (64 * 256 + 64));
   t.scales = (float*)take(sizeof(float) * 2 * kNumSc);
   t.wimg = (unsigned char*)take((size_t)kNumImg * kBlkBytes);
+  t.out3c = (float*)take(sizeof(float) * 2 * 1024);
   t.p0f = (float*)take(sizeof(float) * 2 * B * P * 64);
   t.p0i = (float*)take(sizeof(float) * 2 * B * P * 64);
   t.ftab = (float*)take(sizeof(float) * 2 * B * P * 64);
@@ -979,11 +981,126 @@ __device__ __forceinline__ void q_sine_out3(QEpi& c, float s, const float4* __re
   o2 += (x0 + x1) + (x2 + x3);
 }
 
+#ifndef MOTIF_OUT3_SMEM
+// Output-layer constants in the constant bank: the shared-memory version costs every epilogue warp two broadcast
+// LDS.128 per pair of hidden units (512 B written back to the register file per instruction through the LSU data
+// pipe, the busiest unit of these kernels per ncu: 65 % / 82 %).  From the constant bank they arrive in UNIFORM
+// registers (LDCU.64, 8 B per warp) and FFMA2 takes them as uniform operands.
+__constant__ ulonglong2 c_out3[2][256];  // [0] flow_imnet, [1] synth_net: per pair of units two 16-byte words (layout of q_sine_out3)
+template <int WHICH>
+__device__ __forceinline__ void q_sine_out3_c(QEpi& c, float s, int ch, bool release, float& o0, float& o1, float& o2) {
+  uint32_t r[64];
+  q_take_d(c, r, release);
+  const f32x2 s2 = pack2(s, s);
+  // the chunk index is warp-uniform, but only a warp reduction PROVES it to ptxas (REDUX writes a uniform register):
+  // with a per-thread index the loads become LDC.64 into vector registers instead of LDCU.64 into uniform ones
+  const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const char*>(c_out3[WHICH]) + __reduce_max_sync(0xffffffffu, 1024 * ch));
+  f32x2 p0[2] = {0ull, 0ull}, p1[2] = {0ull, 0ull}, p2[2] = {0ull, 0ull};
+#pragma unroll
+  for (int pr = 0; pr < 32; ++pr) {
+    const ulonglong2 wa = w2[2 * pr], wb = w2[2 * pr + 1];
+    float a0, a1;
+    unpack2(ffma2(pack2(__uint_as_float(r[2 * pr]), __uint_as_float(r[2 * pr + 1])), s2, wa.x), a0, a1);
+    const f32x2 v = pack2(__sinf(a0), __sinf(a1));
+    p0[pr & 1] = ffma2(v, wa.y, p0[pr & 1]);
+    p1[pr & 1] = ffma2(v, wb.x, p1[pr & 1]);
+    p2[pr & 1] = ffma2(v, wb.y, p2[pr & 1]);
+  }
+  float x0, x1, x2, x3;
+  unpack2(p0[0], x0, x1), unpack2(p0[1], x2, x3);
+  o0 += (x0 + x1) + (x2 + x3);
+  unpack2(p1[0], x0, x1), unpack2(p1[1], x2, x3);
+  o1 += (x0 + x1) + (x2 + x3);
+  unpack2(p2[0], x0, x1), unpack2(p2[1], x2, x3);
+  o2 += (x0 + x1) + (x2 + x3);
+}
+// staging[which][pair][8] from the weight pack (same values the kernels put into shared memory)
+__global__ void out3_consts_kernel(const float* __restrict__ wp, float* __restrict__ staging) {
+  const int pr = threadIdx.x & 127, which = threadIdx.x >> 7, i = 2 * pr;
+  const int ob = which ? WeightPack::s_b3 : WeightPack::f_b2, oa = which ? WeightPack::s_a4 : WeightPack::f_a3;
+  float* d = staging + which * 1024 + 8 * pr;
+  d[0] = wp[ob + i] * kOmega, d[1] = wp[ob + i + 1] * kOmega, d[2] = wp[oa + i], d[3] = wp[oa + i + 1];
+  d[4] = wp[oa + 256 + i], d[5] = wp[oa + 256 + i + 1], d[6] = wp[oa + 512 + i], d[7] = wp[oa + 512 + i + 1];
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // flow_imnet + binning of the three forward splats, quad pipeline.  Work item = (reference frame, 128-pixel tile).
 // ------------------------------------------------------------------------------------------------------
 __constant__ QStep kQProgF[5] = {{0, 1}, {1, 1}, {2, 2}, {3, 2}, {4, 2}};
 using QSmemF = QSmem<5>;
+// The three forward splats of one source pixel (one thread), binned: flow / z scaling (Ours.py:794), footprint, one list slot
+// per covered destination, side sums and max by red.global.  A real function call, not inlined: its uniform operands (sizes,
+// array bases) then live in its own frame instead of occupying uniform registers across the MLP epilogues of the caller --
+// with them inlined ptxas has no uniform registers left for the output-layer constants and loads those per thread.
+struct ScatterCtx {
+  int items_per_t, n0, B, b, N, qs, WW, HH;
+  float flow_scale, alpha;
+  float* flow_out;
+  int* bin_count;
+  float* side;
+  float* zmax;
+  uint2* bin_ent;
+  const float* Y;
+  float* spill;
+};
+__device__ __noinline__ void scatter_item(const ScatterCtx& cx, int item, int row, float dx, float dy, float zraw) {
+  const int qs = cx.qs, WW = cx.WW;
+  const int nl = item / cx.items_per_t, rem = item - nl * cx.items_per_t;
+  const int n = cx.n0 + nl;
+  const int rb = (rem & 1) * cx.B + cx.b;
+  const int q = (rem >> 1) * 128 + row;
+  if (q >= qs) return;
+  const int qy = q / WW, qx = q - qy * WW;
+  // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
+  const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), cx.flow_scale);
+  const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), cx.flow_scale);
+  const float z = __fmul_rn(fmaxf(zraw, 0.0f), cx.alpha);
+  const float e = expf(z);
+  if (cx.flow_out != nullptr) {
+    float* fo = cx.flow_out + ((size_t)(rb * cx.N + n) * 2) * qs + q;
+    fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), cx.flow_scale);
+    fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), cx.flow_scale);
+  }
+  const Footprint f = footprint(qx, qy, fx, fy);
+  if (!f.finite) return;
+  const uint32_t id = (uint32_t)((size_t)rb * qs + q);
+  const size_t dbase = ((size_t)nl * cx.B + cx.b) * qs;  // this timestamp's destination arrays
+  const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
+  int slot[4];
+  size_t dd[4];
+  bool ok[4];
+  // all four slot requests go out before any of them is consumed
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int cx_ = f.x0 + (k & 1), cy_ = f.y0 + (k >> 1);
+    ok[k] = !((cx_ < 0) | (cx_ >= WW) | (cy_ < 0) | (cy_ >= cx.HH));
+    dd[k] = dbase + (size_t)(ok[k] ? cy_ : 0) * WW + (ok[k] ? cx_ : 0);
+    slot[k] = ok[k] ? atomicAdd(cx.bin_count + dd[k], 1) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (!ok[k]) continue;
+    const size_t d = dd[k];
+    const float wk = f.w[k];
+    const float we = __fmul_rn(e, wk);
+    red_add_v4(cx.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
+    // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
+    if (we > 1.0f) red_max_nonneg(cx.zmax + d, we);
+    if (slot[k] < kSlots) {
+      cx.bin_ent[d * kSlots + slot[k]] = make_uint2(id, __float_as_uint(we));
+    } else {
+      const float4* y4 = reinterpret_cast<const float4*>(cx.Y + (size_t)id * 64);
+      float* sp = cx.spill + d * 64;
+#pragma unroll 4
+      for (int j4 = 0; j4 < 16; ++j4) {
+        const float4 y = __ldg(y4 + j4);
+        red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
+      }
+    }
+  }
+}
+
 // consts: [0,256) unused  [256,320) 30 b1  [320,1344) output weights per pair of hidden units (see q_sine_out3)  [1344,1347) b3
 //         [1348] s1 [1349] s2   [2048 + 256 nl, +256) e0 of timestamp nl, per pair of units (see q_table_layer0)
 // Work item = (timestamp of the group, reference frame, 128-pixel tile), timestamp-major.
@@ -996,6 +1113,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
   const int items_per_t = 2 * ((qs + 127) / 128);
   const int n_items = nt * items_per_t;
   const float* wp = sc.wpack;
+  __shared__ ScatterCtx s_ctx;
+  if (threadIdx.x == 0) {
+    s_ctx.items_per_t = items_per_t, s_ctx.n0 = n0, s_ctx.B = B, s_ctx.b = b, s_ctx.N = N, s_ctx.qs = qs, s_ctx.WW = g.WW, s_ctx.HH = g.HH;
+    s_ctx.flow_scale = g.flow_scale, s_ctx.alpha = alpha, s_ctx.flow_out = flow_out;
+    s_ctx.bin_count = sc.bin_count, s_ctx.side = sc.side, s_ctx.zmax = sc.zmax, s_ctx.bin_ent = sc.bin_ent, s_ctx.Y = sc.Y, s_ctx.spill = sc.spill;
+  }
   for (int i = threadIdx.x; i < 32 * nt; i += blockDim.x) {  // pair of units (2 pr, 2 pr + 1) of timestamp i / 32
     const int pr = i & 31;
     const float t = time_of(times, i >> 5);
@@ -1005,12 +1128,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
     dst[1] = make_float4(e.w * kOmega, f.w * kOmega, 0.f, 0.f);
   }
   for (int i = threadIdx.x; i < 64; i += blockDim.x) sm.consts[256 + i] = wp[WeightPack::f_b1 + i] * kOmega;
+#ifdef MOTIF_OUT3_SMEM
   for (int pr = threadIdx.x; pr < 128; pr += blockDim.x) {
     const int i = 2 * pr;
     float4* dst = reinterpret_cast<float4*>(sm.consts + 320) + 2 * pr;
     dst[0] = make_float4(wp[WeightPack::f_b2 + i] * kOmega, wp[WeightPack::f_b2 + i + 1] * kOmega, wp[WeightPack::f_a3 + i], wp[WeightPack::f_a3 + i + 1]);
     dst[1] = make_float4(wp[WeightPack::f_a3 + 256 + i], wp[WeightPack::f_a3 + 256 + i + 1], wp[WeightPack::f_a3 + 512 + i], wp[WeightPack::f_a3 + 512 + i + 1]);
   }
+#endif
   if (threadIdx.x < 3) sm.consts[1344 + threadIdx.x] = wp[WeightPack::f_b3 + threadIdx.x];
   if (threadIdx.x < 2) sm.consts[1348 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScF1 + threadIdx.x];
   q_setup(sm.bars);
@@ -1031,7 +1156,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
     if (g_issuer_mode != 0) q_issuer<3>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 3));
   } else {
     QEpi c = q_make_epi(sm.bars);
+#ifdef MOTIF_OUT3_SMEM
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
+#endif
     const float s1 = sm.consts[1348], s2 = sm.consts[1349];
     const int row = c.quad * 32 + lane;
     const int n_iters = q_iters(n_items, c.tile);
@@ -1040,61 +1167,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
     // of holding the tile's four warps back from it.
     float p_dx = 0.f, p_dy = 0.f, p_z = 0.f;
     int p_item = -1;
-    auto scatter = [&](int item, float dx, float dy, float zraw) {
-      const int nl = item / items_per_t, rem = item - nl * items_per_t;
-      const int n = n0 + nl;
-      const int rb = (rem & 1) * B + b;
-      const int q = (rem >> 1) * 128 + row;
-      if (q >= qs) return;
-      const int qy = q / g.WW, qx = q - qy * g.WW;
-      // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
-      const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
-      const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
-      const float z = __fmul_rn(fmaxf(zraw, 0.0f), alpha);
-      const float e = expf(z);
-      if (flow_out != nullptr) {
-        float* fo = flow_out + ((size_t)(rb * N + n) * 2) * qs + q;
-        fo[0] = __fdiv_rn(__fdiv_rn(fx, 20.0f), g.flow_scale);
-        fo[qs] = __fdiv_rn(__fdiv_rn(fy, 20.0f), g.flow_scale);
-      }
-      const Footprint f = footprint(qx, qy, fx, fy);
-      if (!f.finite) return;
-      const uint32_t id = (uint32_t)((size_t)rb * qs + q);
-      const size_t dbase = ((size_t)nl * B + b) * qs;  // this timestamp's destination arrays
-      const float edx = __fmul_rn(dx, e), edy = __fmul_rn(dy, e);
-      int slot[4];
-      size_t dd[4];
-      bool ok[4];
-      // all four slot requests go out before any of them is consumed
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int cx = f.x0 + (k & 1), cy = f.y0 + (k >> 1);
-        ok[k] = !((cx < 0) | (cx >= g.WW) | (cy < 0) | (cy >= g.HH));
-        dd[k] = dbase + (size_t)(ok[k] ? cy : 0) * g.WW + (ok[k] ? cx : 0);
-        slot[k] = ok[k] ? atomicAdd(sc.bin_count + dd[k], 1) : 0;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!ok[k]) continue;
-        const size_t d = dd[k];
-        const float wk = f.w[k];
-        const float we = __fmul_rn(e, wk);
-        red_add_v4(sc.side + d * 4, __fmul_rn(edx, wk), __fmul_rn(edy, wk), we, 1.0f);
-        // the max splat starts at 1.0 (softsplat_max_cp.py:254): only a candidate above 1 can change it
-        if (we > 1.0f) red_max_nonneg(sc.zmax + d, we);
-        if (slot[k] < kSlots) {
-          sc.bin_ent[d * kSlots + slot[k]] = make_uint2(id, __float_as_uint(we));
-        } else {
-          const float4* y4 = reinterpret_cast<const float4*>(sc.Y + (size_t)id * 64);
-          float* sp = sc.spill + d * 64;
-#pragma unroll 4
-          for (int j4 = 0; j4 < 16; ++j4) {
-            const float4 y = __ldg(y4 + j4);
-            red_add_v4(sp + 4 * j4, y.x * we, y.y * we, y.z * we, y.w * we);
-          }
-        }
-      }
-    };
+    auto scatter = [&](int item, float dx, float dy, float zraw) { scatter_item(s_ctx, item, row, dx, dy, zraw); };
     for (int it = 0; it < n_iters; ++it) {
       TRACE_Q(c, 1);
       const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
@@ -1112,7 +1185,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       q_sine_epilogue(c, s1, sm.consts + 256);
       float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
 #pragma unroll 1
+#ifndef MOTIF_OUT3_SMEM
+      for (int ch = 0; ch < 4; ++ch) q_sine_out3_c<0>(c, s2, ch, ch < 3, dx, dy, zraw);
+#else
       for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
+#endif
       TRACE_Q(c, 2);
       p_dx = dx, p_dy = dy, p_z = zraw, p_item = item;
     }
@@ -1340,12 +1417,14 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
     sm.consts[i] = wp[WeightPack::s_b1 + i] * kOmega;
     sm.consts[64 + i] = wp[WeightPack::s_b2 + i] * kOmega;
   }
+#ifdef MOTIF_OUT3_SMEM
   for (int pr = threadIdx.x; pr < 128; pr += blockDim.x) {
     const int i = 2 * pr;
     float4* dst = reinterpret_cast<float4*>(sm.consts + 128) + 2 * pr;
     dst[0] = make_float4(wp[WeightPack::s_b3 + i] * kOmega, wp[WeightPack::s_b3 + i + 1] * kOmega, wp[WeightPack::s_a4 + i], wp[WeightPack::s_a4 + i + 1]);
     dst[1] = make_float4(wp[WeightPack::s_a4 + 256 + i], wp[WeightPack::s_a4 + 256 + i + 1], wp[WeightPack::s_a4 + 512 + i], wp[WeightPack::s_a4 + 512 + i + 1]);
   }
+#endif
   if (threadIdx.x < 3) {
     sm.consts[1152 + threadIdx.x] = wp[WeightPack::s_b4 + threadIdx.x];
     sm.consts[1156 + threadIdx.x] = kOmega * sc.scales[kNumSc + kScS1 + threadIdx.x];
@@ -1368,7 +1447,9 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
     if (g_issuer_mode != 0) q_issuer<3>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 3));
   } else {
     QEpi c = q_make_epi(sm.bars);
+#ifdef MOTIF_OUT3_SMEM
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
+#endif
     const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
     const int n_iters = q_iters(n_items, c.tile);
     for (int it = 0; it < n_iters; ++it) {
@@ -1394,7 +1475,11 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
       q_sine_epilogue(c, s2, sm.consts + 64);
       float o0 = sm.consts[1152], o1 = sm.consts[1153], o2 = sm.consts[1154];
 #pragma unroll 1
+#ifndef MOTIF_OUT3_SMEM
+      for (int ch = 0; ch < 4; ++ch) q_sine_out3_c<1>(c, s3, ch, ch < 3, o0, o1, o2);
+#else
       for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s3, cw + 64 * ch, ch < 3, o0, o1, o2);
+#endif
       TRACE_Q(c, 2);
       int qy, qx;
       if (a0_position(a, blocks_x, g.HH, g.WW, qy, qx)) {
@@ -1442,6 +1527,11 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
   for (int c = 0; c < 4; ++c) add(0, Wp::s_a3, 64, 64 * c, 0, kScS3);
   pack_images_kernel<<<kNumImg, 256, 0, st>>>(ij, sc.wpack, sc.fold, sc.scales, sc.wimg);
   MOTIF_LAUNCHED("pack_images_kernel");
+#ifndef MOTIF_OUT3_SMEM
+  out3_consts_kernel<<<1, 256, 0, st>>>(sc.wpack, sc.out3c);
+  MOTIF_LAUNCHED("out3_consts_kernel");
+  MOTIF_CUDA(cudaMemcpyToSymbolAsync(c_out3, sc.out3c, sizeof(c_out3), 0, cudaMemcpyDeviceToDevice, st));
+#endif
   // LR tables
   LrJobs lj;
   int nj = 0;
