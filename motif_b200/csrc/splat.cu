@@ -311,7 +311,12 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restri
 // not fit (strongly diverging flow) and planes whose rows are not 16-byte aligned take the direct path above.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 8;    // destination tile
-constexpr int kRW = 64, kRH = 16;   // staged source window (floats x rows): 16 x 16 16-byte columns, one per thread
+#ifndef MOTIF_SPLAT_RW
+#define MOTIF_SPLAT_RW 64
+#define MOTIF_SPLAT_RH 16
+#endif
+constexpr int kRW = MOTIF_SPLAT_RW, kRH = MOTIF_SPLAT_RH;   // staged source window (floats x rows): at most 256 16-byte columns, one per thread
+static_assert((kRW / 4) * kRH <= 256 && kRW % 4 == 0, "one 16-byte column of the window per thread");
 constexpr int kPlane = kRH * kRW + 4; // floats per staged channel plane: the window + a zero word (16-byte padded)
 constexpr int kStages = 3;          // staged chunks: one being read, kStages - 1 in flight (>= 3: one barrier per chunk suffices)
 constexpr int kTiledSmem = kStages * 8 * kPlane * (int)sizeof(float);
@@ -372,7 +377,10 @@ __device__ __forceinline__ void tile_channels(const float* __restrict__ stage, f
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) splat_gather_tiled_kernel(const float* __restrict__ in, const float* __restrict__ metric,
+#ifndef MOTIF_SPLAT_CTAS
+#define MOTIF_SPLAT_CTAS 2
+#endif
+__global__ void __launch_bounds__(256, MOTIF_SPLAT_CTAS) splat_gather_tiled_kernel(const float* __restrict__ in, const float* __restrict__ metric,
                                                                  float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
   extern __shared__ __align__(16) float buf_raw[];  // [kStages][kCH][kPlane]
   float(*buf)[kCH * kPlane] = reinterpret_cast<float(*)[kCH * kPlane]>(buf_raw);
