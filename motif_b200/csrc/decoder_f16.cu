@@ -109,6 +109,7 @@ struct Scratch {
   float* fold;              // [64][256] W0a*W3 then [64] W0a*b3
   float* scales;            // [kNumSc] power-of-two weight scales, then [kNumSc] their inverses
   unsigned char* wimg;      // [kNumImg] fp16 block images
+  int* qctr;                // [8] work-item counters of the persistent quad kernels (zeroed before each launch)
   float* out3c;             // [2][1024] staging of the output-layer constants (flow_imnet, synth_net) for the constant bank
   float* p0f;               // [2B][P][64]  30 * W0f[:, :64] * flow_feat
   float* p0i;               // [2B][P][64]  30 * W0i[:, :64] * feat
@@ -140,6 +141,7 @@ static int layout(int B, int NT, int H, int W, int HH, int WW, Scratch* s, char*
   t.scales = (float*)take(sizeof(float) * 2 * kNumSc);
   t.wimg = (unsigned char*)take((size_t)kNumImg * kBlkBytes);
   t.out3c = (float*)take(sizeof(float) * 2 * 1024);
+  t.qctr = (int*)take(sizeof(int) * 8);
   t.p0f = (float*)take(sizeof(float) * 2 * B * P * 64);
   t.p0i = (float*)take(sizeof(float) * 2 * B * P * 64);
   t.ftab = (float*)take(sizeof(float) * 2 * B * P * 64);
@@ -726,7 +728,6 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 // Per tile 128 TMEM columns: [0,32) A_hi [32,64) A_lo [64,128) D.  A single accumulator suffices: the epilogue
 // copies all 64 columns into registers and releases D at once, so the next block's MMAs overlap its arithmetic.
 // ======================================================================================================
-__device__ int g_issuer_mode = 1;  // tuning: 1 = an issuer warp per tile (default, measured 1.5% faster), 0 = one polling issuer warp for the four tiles
 constexpr int kQTileCols = 128;
 constexpr uint32_t kQColA = 0, kQColD = 64;
 
@@ -736,6 +737,7 @@ struct QBars {
   uint64_t d_ready[4];  // tcgen05.commit
   uint64_t d_free[4];   // 128 arrivals: accumulator copied into registers
   uint32_t tmem_base;
+  int next_item[4];     // work item of each tile slot (-1: no more), written by the slot's leader thread
 };
 template <int NIMG>
 struct QSmem {
@@ -756,6 +758,7 @@ __device__ __forceinline__ uint32_t q_setup(QBars& bars) {
       mbar_init(&bars.a_ready[t], 128);
       mbar_init(&bars.d_ready[t], 1);
       mbar_init(&bars.d_free[t], 128);
+      bars.next_item[t] = 0;
     }
     fence_mbar_init();
   }
@@ -770,20 +773,56 @@ __device__ __forceinline__ uint32_t q_setup(QBars& bars) {
   return bars.tmem_base;
 }
 
-// number of work items of tile slot `tile` of this CTA: item(it) = 4 * (blockIdx.x + it * gridDim.x) + tile
-__device__ __forceinline__ int q_iters(int n_items, int tile) {
-  const int first = 4 * (int)blockIdx.x + tile, stride = 4 * (int)gridDim.x;
-  return first < n_items ? (n_items - first + stride - 1) / stride : 0;
+// Work items are handed out DYNAMICALLY: the leader thread of a tile slot takes the next item from a global counter
+// (the request for item i + 1 is in flight while item i is processed), publishes it to the slot's other warps through
+// shared memory and a 128-thread named barrier, and to the slot's issuer warp through the first a_ready hand-off of the
+// item.  With the static assignment item = 4 (cta + it * grid) + slot, a slot always served the same reference frame
+// (item parity) and the slots of a CTA finished up to 10 % apart (ncu: that share of the warp samples sat in the final
+// barrier); the last arrival on a_ready with next_item = -1 releases the issuer.
+__device__ __forceinline__ void quad_sync(int tile) { asm volatile("bar.sync %0, 128;" ::"r"(1 + tile) : "memory"); }
+struct QFeed {
+  int* ctr;
+  int n_items;
+  int pending;
+  bool leader;
+};
+__device__ __forceinline__ QFeed q_feed_init(int* ctr, int n_items, bool leader) {
+  QFeed f{ctr, n_items, 0, leader};
+  if (leader) f.pending = atomicAdd(ctr, 1);
+  return f;
 }
-
+// next item of this tile slot, or -1 after releasing the issuer (all 128 threads of the slot call this together)
+__device__ __forceinline__ int q_feed_next(QFeed& f, QBars& bars, int tile) {
+  volatile int* slot = &bars.next_item[tile];
+  if (f.leader) *slot = f.pending < f.n_items ? f.pending : -1;
+  quad_sync(tile);
+  const int item = *slot;
+  if (item < 0) {
+    mbar_arrive(&bars.a_ready[tile]);
+    return -1;
+  }
+  if (f.leader) f.pending = atomicAdd(f.ctr, 1);
+  return item;
+}
+// Static assignment (item = 4 (cta + it * grid) + slot) for a kernel whose slots are balanced anyway (synth_q: the
+// per-item barrier and counter of the dynamic feed cost it 2.6 %); same hand-off to the issuer at the end.
+__device__ __forceinline__ int q_static_next(int& it, int n_items, bool leader, QBars& bars, int tile) {
+  const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + tile;
+  ++it;
+  if (item < n_items) return item;
+  if (leader) *(volatile int*)&bars.next_item[tile] = -1;  // ordered before the leader's own arrival (release)
+  mbar_arrive(&bars.a_ready[tile]);
+  return -1;
+}
 template <int tile, int NSTEPS>
-__device__ __forceinline__ void q_issuer(QBars& bars, const unsigned char* img_base, const QStep (&prog)[NSTEPS], int n_iters) {
+__device__ __forceinline__ void q_issuer_dyn(QBars& bars, const unsigned char* img_base, const QStep (&prog)[NSTEPS]) {
   constexpr uint32_t idesc = idesc_f16(128, 64);
   constexpr uint32_t acol = tile * kQTileCols + kQColA, dcol = tile * kQTileCols + kQColD;
   uint32_t ph_a = 0, ph_f = 0;
   const uint64_t img_desc = smem_desc_sw128(smem_u32(img_base));
+  const volatile int* slot = &bars.next_item[tile];
   mbar_wait(&bars.w_full, 0);
-  for (int it = 0; it < n_iters; ++it) {
+  for (;;) {
 #pragma unroll 1
     for (int s = 0; s < NSTEPS; ++s) {
       const QStep st = prog[s];
@@ -792,6 +831,7 @@ __device__ __forceinline__ void q_issuer(QBars& bars, const unsigned char* img_b
       if (st.wait == 1) {
         mbar_wait(&bars.a_ready[tile], ph_a);
         ph_a ^= 1;
+        if (s == 0 && *slot < 0) return;  // step 0 of every program waits on a_ready
       } else {
         mbar_wait(&bars.d_free[tile], ph_f);
         ph_f ^= 1;
@@ -810,57 +850,6 @@ __device__ __forceinline__ void q_issuer(QBars& bars, const unsigned char* img_b
       }
       __syncwarp();
     }
-  }
-}
-
-// ONE issuer warp serves the four tiles: it polls their hand-off barriers in turn and issues the 12 MMAs of whichever
-// block is ready as one uninterrupted burst.  With an issuer per tile the four bursts interleave in the tensor queue
-// whenever the tiles are in phase, every block then completes at the END of the combined burst, all four epilogues
-// start together and fight for the same MUFU pipes while the tensor pipe idles: the tiles stay in lock step and tensor
-// and MUFU time add up instead of overlapping.  Block-granular FIFO service breaks the lock step: the first tile leaves
-// for its epilogue while the others are still queued.
-template <int tile, int NSTEPS>
-__device__ __forceinline__ bool q_poll_tile(QBars& bars, uint64_t img_desc, const QStep (&prog)[NSTEPS], int& s, uint32_t& ph_a, uint32_t& ph_f) {
-  constexpr uint32_t idesc = idesc_f16(128, 64);
-  constexpr uint32_t acol = tile * kQTileCols + kQColA, dcol = tile * kQTileCols + kQColD;
-  const QStep st = prog[s];
-  uint64_t* bar = st.wait == 1 ? &bars.a_ready[tile] : &bars.d_free[tile];
-  const uint32_t parity = st.wait == 1 ? ph_a : ph_f;
-  if (!__any_sync(0xffffffffu, mbar_test(bar, parity))) return false;
-  if (st.wait == 1) ph_a ^= 1; else ph_f ^= 1;
-  tc_fence_after();
-  const uint64_t bhi = img_desc + (uint64_t)(st.img * (kBlkBytes >> 4));
-  const uint64_t blo = bhi + (kBlkHalf >> 4);
-  if (elect_one()) {
-#pragma unroll
-    for (int term = 0; term < 3; ++term) {
-      const uint32_t a = (term == 1) ? acol + 32 : acol;
-      const uint64_t b = (term == 2) ? blo : bhi;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) mma_f16_ts(dcol, a + ks * 8, b + 2 * ks, idesc, (term | ks) != 0);
-    }
-    mma_commit(&bars.d_ready[tile]);
-  }
-  __syncwarp();
-  s = s + 1 == NSTEPS ? 0 : s + 1;
-  return true;
-}
-
-template <int NSTEPS>
-__device__ __forceinline__ void q_issuer_all(QBars& bars, const unsigned char* img_base, const QStep (&prog)[NSTEPS], int n_items) {
-  const uint64_t img_desc = smem_desc_sw128(smem_u32(img_base));
-  int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  uint32_t pa0 = 0, pa1 = 0, pa2 = 0, pa3 = 0, pf0 = 0, pf1 = 0, pf2 = 0, pf3 = 0;
-  // blocks left per tile
-  int r0 = q_iters(n_items, 0) * NSTEPS, r1 = q_iters(n_items, 1) * NSTEPS, r2 = q_iters(n_items, 2) * NSTEPS, r3 = q_iters(n_items, 3) * NSTEPS;
-  mbar_wait(&bars.w_full, 0);
-  while ((r0 | r1 | r2 | r3) != 0) {
-    bool any = false;
-    if (r0 != 0 && q_poll_tile<0>(bars, img_desc, prog, s0, pa0, pf0)) --r0, any = true;
-    if (r1 != 0 && q_poll_tile<1>(bars, img_desc, prog, s1, pa1, pf1)) --r1, any = true;
-    if (r2 != 0 && q_poll_tile<2>(bars, img_desc, prog, s2, pa2, pf2)) --r2, any = true;
-    if (r3 != 0 && q_poll_tile<3>(bars, img_desc, prog, s3, pa3, pf3)) --r3, any = true;
-    if (!any) __nanosleep(40);
   }
 }
 
@@ -1146,14 +1135,13 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       for (int i = 0; i < 5; ++i) bulk_g2s(&sm.img[i][0], sc.wimg + (size_t)(kImgF1 + i) * kBlkBytes, kBlkBytes, &sm.bars.w_full);
     }
     __syncwarp();
-    if (g_issuer_mode == 0) q_issuer_all(sm.bars, &sm.img[0][0], kQProgF, n_items);
-    else q_issuer<0>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 0));
+    q_issuer_dyn<0>(sm.bars, &sm.img[0][0], kQProgF);
   } else if (warp == 1) {
-    if (g_issuer_mode != 0) q_issuer<1>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 1));
+    q_issuer_dyn<1>(sm.bars, &sm.img[0][0], kQProgF);
   } else if (warp == 2) {
-    if (g_issuer_mode != 0) q_issuer<2>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 2));
+    q_issuer_dyn<2>(sm.bars, &sm.img[0][0], kQProgF);
   } else if (warp == 3) {
-    if (g_issuer_mode != 0) q_issuer<3>(sm.bars, &sm.img[0][0], kQProgF, q_iters(n_items, 3));
+    q_issuer_dyn<3>(sm.bars, &sm.img[0][0], kQProgF);
   } else {
     QEpi c = q_make_epi(sm.bars);
 #ifdef MOTIF_OUT3_SMEM
@@ -1161,16 +1149,17 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
 #endif
     const float s1 = sm.consts[1348], s2 = sm.consts[1349];
     const int row = c.quad * 32 + lane;
-    const int n_iters = q_iters(n_items, c.tile);
+    QFeed feed = q_feed_init(sc.qctr + 0, n_items, c.quad == 0 && lane == 0);
     // The three splats of item i are issued AFTER the first-layer operand of item i + 1 has been published: their atomics
     // (a return-value round trip through L2 before the dependent list store) then overlap that item's first MMA instead
     // of holding the tile's four warps back from it.
     float p_dx = 0.f, p_dy = 0.f, p_z = 0.f;
     int p_item = -1;
     auto scatter = [&](int item, float dx, float dy, float zraw) { scatter_item(s_ctx, item, row, dx, dy, zraw); };
-    for (int it = 0; it < n_iters; ++it) {
+    for (;;) {
+      const int item = q_feed_next(feed, sm.bars, c.tile);
+      if (item < 0) break;
       TRACE_Q(c, 1);
-      const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
       const int nl = item / items_per_t, rem = item - nl * items_per_t;
       const float4* e0 = reinterpret_cast<const float4*>(sm.consts + 2048 + 256 * nl);
       const int rb = (rem & 1) * B + b;
@@ -1437,24 +1426,24 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
       for (int i = 0; i < 6; ++i) bulk_g2s(&sm.img[i][0], sc.wimg + (size_t)(kImgS1 + i) * kBlkBytes, kBlkBytes, &sm.bars.w_full);
     }
     __syncwarp();
-    if (g_issuer_mode == 0) q_issuer_all(sm.bars, &sm.img[0][0], kQProgS, n_items);
-    else q_issuer<0>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 0));
+    q_issuer_dyn<0>(sm.bars, &sm.img[0][0], kQProgS);
   } else if (warp == 1) {
-    if (g_issuer_mode != 0) q_issuer<1>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 1));
+    q_issuer_dyn<1>(sm.bars, &sm.img[0][0], kQProgS);
   } else if (warp == 2) {
-    if (g_issuer_mode != 0) q_issuer<2>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 2));
+    q_issuer_dyn<2>(sm.bars, &sm.img[0][0], kQProgS);
   } else if (warp == 3) {
-    if (g_issuer_mode != 0) q_issuer<3>(sm.bars, &sm.img[0][0], kQProgS, q_iters(n_items, 3));
+    q_issuer_dyn<3>(sm.bars, &sm.img[0][0], kQProgS);
   } else {
     QEpi c = q_make_epi(sm.bars);
 #ifdef MOTIF_OUT3_SMEM
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
 #endif
     const float s1 = sm.consts[1156], s2 = sm.consts[1157], s3 = sm.consts[1158];
-    const int n_iters = q_iters(n_items, c.tile);
-    for (int it = 0; it < n_iters; ++it) {
+    int it = 0;
+    for (;;) {
+      const int item = q_static_next(it, n_items, c.quad == 0 && lane == 0, sm.bars, c.tile);
+      if (item < 0) break;
       TRACE_Q(c, 1);
-      const int item = 4 * ((int)blockIdx.x + it * (int)gridDim.x) + c.tile;
       const int nl = item / items_per_t;
       const int n = n0 + nl;
       const int a = (item - nl * items_per_t) * 128 + c.quad * 32 + lane;
@@ -1615,10 +1604,6 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       const uint32_t hint = (uint32_t)atoi(getenv("MOTIF_MBAR_HINT"));
       MOTIF_CUDA(cudaMemcpyToSymbol(tc::c_mbar_hint, &hint, sizeof(hint)));
     }
-    if (getenv("MOTIF_ISSUER_MODE")) {
-      const int mode = atoi(getenv("MOTIF_ISSUER_MODE"));
-      MOTIF_CUDA(cudaMemcpyToSymbol(g_issuer_mode, &mode, sizeof(int)));
-    }
     attr_done = true;
   }
   // arm the destination accumulators (a no-op when the previous decode on this workspace completed, see arm_kernel)
@@ -1644,6 +1629,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       const int nt = a->n_end - n0 < NT ? a->n_end - n0 : NT;
       Times times;
       for (int i = 0; i < kMaxGroup; ++i) times.t[i] = i < nt ? a->target_t[b * g.N + n0 + i] : 0.0f;
+      MOTIF_CUDA(cudaMemsetAsync(sc.qctr, 0, sizeof(int) * 8, st));  // work-item counter of flow_bin_q
       {
         if (int rc = trace_select(1, st)) return rc;
         ProfScope prof("flow_bin_f16_kernel", st);
