@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MOTIF_ABI_VERSION 2
+#define MOTIF_ABI_VERSION 3
 
 #define MOTIF_E_BADARG (-1)   /* null pointer, non-positive size, unknown mode        */
 #define MOTIF_E_WORKSPACE (-2) /* workspace smaller than the *_workspace_bytes() answer */
@@ -140,6 +140,9 @@ typedef struct {
   float* dbg_pre0;     /* [B*N, 64, HH, WW] synth_net layer-0 pre-activation (synth_in * W0^T + b0); f16x3 only */
   int n_begin, n_end;  /* timestamps [n_begin, n_end) of each clip are decoded (sharding) */
   int precision;       /* MOTIF_PRECISION_*: arithmetic of the three SIREN MLPs               */
+  int local_ensemble;  /* LunaTokis.local_ensemble (Ours.py:453, 660-663, 754-764): 0 as shipped = one nearest latent;
+                        * 1 = the four shifted latents blended by diagonally swapped area weights.  Implemented by
+                        * MOTIF_PRECISION_FP32 only (other precisions return MOTIF_E_UNSUPPORTED).       */
 } motif_decode_t;
 
 /* MLP arithmetic.  F16X3 (default of the Python mirror): tcgen05 kind::f16, every fp32 operand split into two

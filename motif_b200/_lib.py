@@ -73,6 +73,7 @@ class DecodeT(Structure):
         ("dbg_pre0", c_void_p),
         ("n_begin", c_int), ("n_end", c_int),
         ("precision", c_int),
+        ("local_ensemble", c_int),
     ]
 
 

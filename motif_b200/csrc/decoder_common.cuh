@@ -37,9 +37,46 @@ __device__ __forceinline__ Query make_query(int qy, int qx, const motif_geom_t& 
   return q;
 }
 
+// Local ensemble (LunaTokis.local_ensemble = True; False as shipped, Ours.py:453): the query is evaluated at the four
+// latents reached by shifting the coordinate by (v0 / H, v1 / W), v in {-1, +1}^2 (Ours.py:660-663, 686-689), and
+// the four predictions are blended with the area weights of the DIAGONALLY opposite latent (Ours.py:754-764).
+// The shift `v * r + 1e-6` is formed in python double (r = 2 / size / 2) and cast to fp32 by the in-place add.
+__device__ __forceinline__ Query make_query_shifted(int qy, int qx, const motif_geom_t& g, int v0, int v1) {
+  const float lo = (float)(-1 + 1e-6), hi = (float)(1 - 1e-6);
+  const float hy = __ldg(g.seq_hh + qy), hx = __ldg(g.seq_ww + qx);
+  const float s0 = (float)__dadd_rn(__dmul_rn((double)v0, __ddiv_rn(__ddiv_rn(2.0, (double)g.H), 2.0)), 1e-6);
+  const float s1 = (float)__dadd_rn(__dmul_rn((double)v1, __ddiv_rn(__ddiv_rn(2.0, (double)g.W), 2.0)), 1e-6);
+  Query q;
+  q.cy = fminf(fmaxf(__fadd_rn(hy, s0), lo), hi);
+  q.cx = fminf(fmaxf(__fadd_rn(hx, s1), lo), hi);
+  q.iy = nearest_index(q.cy, g.H);
+  q.ix = nearest_index(q.cx, g.W);
+  q.rel_y = __fmul_rn(__fsub_rn(hy, __ldg(g.seq_h + q.iy)), (float)g.H);
+  q.rel_x = __fmul_rn(__fsub_rn(hx, __ldg(g.seq_w + q.ix)), (float)g.W);
+  return q;
+}
+// shift k of the reference's loop nest `for vx in [-1, 1]: for vy in [-1, 1]` (vx moves coordinate 0 = y)
+__device__ __forceinline__ Query ensemble_query(int qy, int qx, const motif_geom_t& g, int k) {
+  return make_query_shifted(qy, qx, g, (k >> 1) ? 1 : -1, (k & 1) ? 1 : -1);
+}
+// w[k] = area[3 - k] / (area[0] + area[1] + area[2] + area[3]),  area = |rel_y * rel_x| + 1e-9
+__device__ __forceinline__ void ensemble_weights(int qy, int qx, const motif_geom_t& g, float (&w)[4]) {
+  float area[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const Query q = ensemble_query(qy, qx, g, k);
+    area[k] = __fadd_rn(fabsf(__fmul_rn(q.rel_y, q.rel_x)), 1e-9f);
+  }
+  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(area[0], area[1]), area[2]), area[3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[k] = __fdiv_rn(area[3 - k], tot);
+}
+__device__ __forceinline__ float pick4(const float (&w)[4], int k) { return k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3])); }
+
 // -----------------------------------------------------------------------------------------------------
 // Scratch layout (all fp32, pixel-major so that one pixel's channels are contiguous):
 //   imf      [2B][qs][64]   imnet output per reference frame (clip-invariant)
+//   imf_low  [2B][qs][64]   local ensemble only: the blended nearest latents (q_feat_low, Ours.py:723, 762)
 //   acc_main [B][qs][128]   sum-splat accumulator of one timestamp: imnet' (64) | nearest feat' (64),
 //                           both references accumulate into the same cell (Ours.py:811 sums them anyway)
 //   acc_side [B][qs][4]     (sum e*dx, sum e*dy, sum e [the normaliser], count)
@@ -48,6 +85,7 @@ __device__ __forceinline__ Query make_query(int qy, int qx, const motif_geom_t& 
 // -----------------------------------------------------------------------------------------------------
 struct DecodeScratch {
   float* imf;
+  float* imf_low;
   float* acc_main;
   float* acc_side;
   float* acc_max;

@@ -73,8 +73,9 @@ __device__ __forceinline__ void sine_layer64(const float* __restrict__ W, const 
 // ---------------------------------------------------------------------------------------------------
 // imnet: 66 -> 64 -> 64 -> 256 -> 64  (Ours.py:471, 737)
 // ---------------------------------------------------------------------------------------------------
+template <bool ENS>
 __global__ void __launch_bounds__(kThreads, 1) imnet_kernel(motif_geom_t g, const float* __restrict__ feat, const float* __restrict__ wp,
-                                                           float* __restrict__ imf) {
+                                                           float* __restrict__ imf, float* __restrict__ imf_low) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ActBuf& X = *reinterpret_cast<ActBuf*>(smem_raw);
   ActBuf& Y = *reinterpret_cast<ActBuf*>(smem_raw + sizeof(ActBuf));
@@ -82,55 +83,81 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_kernel(motif_geom_t g, cons
   const int q = blockIdx.x * kThreads + threadIdx.x;
   if (q >= qs) return;
   const int rb = blockIdx.y;  // r*B + b
-  const Query qu = make_query(q / g.WW, q % g.WW, g);
-  float h[64];
-  load_row64(feat + ((size_t)rb * g.H * g.W + (size_t)qu.iy * g.W + qu.ix) * 64, h);
-  // layer 0: 64 gathered features on the FMA tile, rel_y / rel_x as rank-1 terms
-  for (int j0 = 0; j0 < 64; j0 += 16) {
-    float acc[16];
-    dense16(wp + WeightPack::i_a0, 64, j0, h, acc);
+  const int qy = q / g.WW, qx = q % g.WW;
+  float ew[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+  if (ENS) ensemble_weights(qy, qx, g, ew);
+  float4* dst = reinterpret_cast<float4*>(imf + ((size_t)rb * qs + q) * 64);
+  float4* dst_low = ENS ? reinterpret_cast<float4*>(imf_low + ((size_t)rb * qs + q) * 64) : nullptr;
+#pragma unroll 1
+  for (int k = 0; k < (ENS ? 4 : 1); ++k) {
+    const Query qu = ENS ? ensemble_query(qy, qx, g, k) : make_query(qy, qx, g);
+    const float wk = pick4(ew, k);
+    float h[64];
+    load_row64(feat + ((size_t)rb * g.H * g.W + (size_t)qu.iy * g.W + qu.ix) * 64, h);
+    if (ENS) {  // q_feat_low: ret = ret + feat * (area / tot_area), Ours.py:762 (product and sum rounded separately)
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-      const float4 e = ldg4(wp + WeightPack::i_e0 + 4 * (j0 + jj));
-      X.v[j0 + jj][threadIdx.x] = siren_act(fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, acc[jj])) + e.x);
+      for (int i4 = 0; i4 < 16; ++i4) {
+        const float4 p = k == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : dst_low[i4];
+        dst_low[i4] = make_float4(__fadd_rn(p.x, __fmul_rn(h[4 * i4], wk)), __fadd_rn(p.y, __fmul_rn(h[4 * i4 + 1], wk)),
+                                  __fadd_rn(p.z, __fmul_rn(h[4 * i4 + 2], wk)), __fadd_rn(p.w, __fmul_rn(h[4 * i4 + 3], wk)));
+      }
     }
-  }
-  load_col(X, h);
-  sine_layer64(wp + WeightPack::i_a1, wp + WeightPack::i_b1, h, Y);
-  // layers 2+3 fused: 64 hidden units at a time -> sine -> accumulate the 256 -> 64 output layer
-  float o[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) o[i] = __ldg(wp + WeightPack::i_b3 + i);
-  for (int c = 0; c < 4; ++c) {
-    load_col(Y, h);
+    // layer 0: 64 gathered features on the FMA tile, rel_y / rel_x as rank-1 terms
     for (int j0 = 0; j0 < 64; j0 += 16) {
       float acc[16];
-      dense16(wp + WeightPack::i_a2, 64, 64 * c + j0, h, acc);
+      dense16(wp + WeightPack::i_a0, 64, j0, h, acc);
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) X.v[j0 + jj][threadIdx.x] = siren_act(acc[jj] + __ldg(wp + WeightPack::i_b2 + 64 * c + j0 + jj));
+      for (int jj = 0; jj < 16; ++jj) {
+        const float4 e = ldg4(wp + WeightPack::i_e0 + 4 * (j0 + jj));
+        X.v[j0 + jj][threadIdx.x] = siren_act(fmaf(e.z, qu.rel_x, fmaf(e.y, qu.rel_y, acc[jj])) + e.x);
+      }
     }
     load_col(X, h);
-    for (int i0 = 0; i0 < 64; i0 += 16) {
-      float acc[16];
-      dense16(wp + WeightPack::i_a3 + 64 * c, 256, i0, h, acc);
-      // o[] must be indexed statically: unrolled select over the four 16-wide output groups
+    sine_layer64(wp + WeightPack::i_a1, wp + WeightPack::i_b1, h, Y);
+    // layers 2+3 fused: 64 hidden units at a time -> sine -> accumulate the 256 -> 64 output layer
+    float o[64];
 #pragma unroll
-      for (int grp = 0; grp < 4; ++grp)
-        if (i0 == 16 * grp) {
+    for (int i = 0; i < 64; ++i) o[i] = __ldg(wp + WeightPack::i_b3 + i);
+    for (int c = 0; c < 4; ++c) {
+      load_col(Y, h);
+      for (int j0 = 0; j0 < 64; j0 += 16) {
+        float acc[16];
+        dense16(wp + WeightPack::i_a2, 64, 64 * c + j0, h, acc);
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) o[16 * grp + jj] += acc[jj];
-        }
+        for (int jj = 0; jj < 16; ++jj) X.v[j0 + jj][threadIdx.x] = siren_act(acc[jj] + __ldg(wp + WeightPack::i_b2 + 64 * c + j0 + jj));
+      }
+      load_col(X, h);
+      for (int i0 = 0; i0 < 64; i0 += 16) {
+        float acc[16];
+        dense16(wp + WeightPack::i_a3 + 64 * c, 256, i0, h, acc);
+        // o[] must be indexed statically: unrolled select over the four 16-wide output groups
+#pragma unroll
+        for (int grp = 0; grp < 4; ++grp)
+          if (i0 == 16 * grp) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) o[16 * grp + jj] += acc[jj];
+          }
+      }
+    }
+    if (!ENS) {
+#pragma unroll
+      for (int i4 = 0; i4 < 16; ++i4) dst[i4] = make_float4(o[4 * i4], o[4 * i4 + 1], o[4 * i4 + 2], o[4 * i4 + 3]);
+    } else {
+#pragma unroll
+      for (int i4 = 0; i4 < 16; ++i4) {
+        const float4 p = k == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : dst[i4];
+        dst[i4] = make_float4(__fadd_rn(p.x, __fmul_rn(o[4 * i4], wk)), __fadd_rn(p.y, __fmul_rn(o[4 * i4 + 1], wk)),
+                              __fadd_rn(p.z, __fmul_rn(o[4 * i4 + 2], wk)), __fadd_rn(p.w, __fmul_rn(o[4 * i4 + 3], wk)));
+      }
     }
   }
-  float4* dst = reinterpret_cast<float4*>(imf + ((size_t)rb * qs + q) * 64);
-#pragma unroll
-  for (int i4 = 0; i4 < 16; ++i4) dst[i4] = make_float4(o[4 * i4], o[4 * i4 + 1], o[4 * i4 + 2], o[4 * i4 + 3]);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // flow_imnet (67 -> 64 -> 64 -> 256 -> 3, Ours.py:470, 736) + the three forward splats of both references
 // (Ours.py:777-806; softsplat_cp.py:320-347 softmax mode, softsplat_max_cp.py, softsplat_count_cp.py).
 // ---------------------------------------------------------------------------------------------------
+template <bool ENS>
 __global__ void __launch_bounds__(kThreads, 1) flow_splat_kernel(motif_geom_t g, int B, int N, int n, float t, float alpha,
                                                                 const float* __restrict__ feat, const float* __restrict__ flow_feat,
                                                                 const float* __restrict__ imf, const float* __restrict__ wp,
@@ -142,12 +169,19 @@ __global__ void __launch_bounds__(kThreads, 1) flow_splat_kernel(motif_geom_t g,
   const int q = blockIdx.x * kThreads + threadIdx.x;
   const bool live = q < qs;
   const int qy = live ? q / g.WW : 0, qx = live ? q % g.WW : 0;
-  const Query qu = make_query(qy, qx, g);
-  const size_t lr = (size_t)qu.iy * g.W + qu.ix;
+  const Query qu0 = make_query(qy, qx, g);
+  const size_t lr = (size_t)qu0.iy * g.W + qu0.ix;
   const int lane = threadIdx.x & 31;
+  float ew[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+  if (ENS) ensemble_weights(qy, qx, g, ew);
 
   for (int r = 0; r < 2; ++r) {
     const int rb = r * B + b;
+    float bdx = 0.f, bdy = 0.f, bz = 0.f;  // blended prediction (Ours.py:758-764); the single one without the ensemble
+#pragma unroll 1
+    for (int k = 0; k < (ENS ? 4 : 1); ++k) {
+    const Query qu = ENS ? ensemble_query(qy, qx, g, k) : qu0;
+    const size_t lr = (size_t)qu.iy * g.W + qu.ix;
     float dx = 0.f, dy = 0.f, zraw = 0.f;
     if (live) {
       float h[64];
@@ -179,6 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_splat_kernel(motif_geom_t g,
         }
       }
     }
+    if (ENS) {
+      const float wk = pick4(ew, k);
+      bdx = __fadd_rn(bdx, __fmul_rn(dx, wk)), bdy = __fadd_rn(bdy, __fmul_rn(dy, wk)), bz = __fadd_rn(bz, __fmul_rn(zraw, wk));
+    } else {
+      bdx = dx, bdy = dy, bz = zraw;
+    }
+    }
+    const float dx = bdx, dy = bdy, zraw = bz;
     // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha
     const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), g.flow_scale);
     const float fy = __fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale);
@@ -204,7 +246,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_splat_kernel(motif_geom_t g,
 #pragma unroll
       for (int k = 0; k < 4; ++k) w4[k] = __shfl_sync(0xffffffffu, f.w[k], p);
       const float* srow = lane < 16 ? imf + ((size_t)rb * qs + sq) * 64 + 4 * lane
-                                    : feat + ((size_t)rb * g.H * g.W + slr) * 64 + 4 * (lane - 16);
+                          : (ENS ? sc.imf_low + ((size_t)rb * qs + sq) * 64 + 4 * (lane - 16)
+                                 : feat + ((size_t)rb * g.H * g.W + slr) * 64 + 4 * (lane - 16));
       float4 v = ldg4(srow);
       // softsplat_cp.py:332: tenInput * tenMetric.exp() is rounded before the kernel multiplies by the weight
       v.x = __fmul_rn(v.x, se);
@@ -229,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_splat_kernel(motif_geom_t g,
 // ---------------------------------------------------------------------------------------------------
 // blend (Ours.py:810-836) + synth_net (198 -> 64 -> 64 -> 64 -> 256 -> 3, Ours.py:487-491, 839-858) + clamp
 // ---------------------------------------------------------------------------------------------------
+template <bool ENS>
 __global__ void __launch_bounds__(kThreads, 1) synth_kernel(motif_geom_t g, int B, int N, int n, float t, const float* __restrict__ residual,
                                                            const float* __restrict__ wp, DecodeScratch sc, float* __restrict__ rgb,
                                                            float* __restrict__ dbg_in, int b) {
@@ -286,8 +330,25 @@ __global__ void __launch_bounds__(kThreads, 1) synth_kernel(motif_geom_t g, int 
         h[4 * k4 + 2] = __fdiv_rn(v.z, wz);
         h[4 * k4 + 3] = __fdiv_rn(v.w, wz);
       }
-    } else {
+    } else if (!ENS) {
       load_row64(residual + ((size_t)b * g.H * g.W + (size_t)qu.iy * g.W + qu.ix) * 64, h);
+    } else {  // q_residual blended over the four latents (Ours.py:762)
+      float ew[4];
+      ensemble_weights(q / g.WW, q % g.WW, g, ew);
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        const Query qk = ensemble_query(q / g.WW, q % g.WW, g, k);
+        const float wk = pick4(ew, k);
+        const float* row = residual + ((size_t)b * g.H * g.W + (size_t)qk.iy * g.W + qk.ix) * 64;
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+          const float4 v = ldg4(row + 4 * k4);
+          h[4 * k4 + 0] = __fadd_rn(k == 0 ? 0.f : h[4 * k4 + 0], __fmul_rn(v.x, wk));
+          h[4 * k4 + 1] = __fadd_rn(k == 0 ? 0.f : h[4 * k4 + 1], __fmul_rn(v.y, wk));
+          h[4 * k4 + 2] = __fadd_rn(k == 0 ? 0.f : h[4 * k4 + 2], __fmul_rn(v.z, wk));
+          h[4 * k4 + 3] = __fadd_rn(k == 0 ? 0.f : h[4 * k4 + 3], __fmul_rn(v.w, wk));
+        }
+      }
     }
     if (dbg) {
       const int c0 = kb == 0 ? 0 : (kb == 1 ? 66 : 133);
@@ -461,12 +522,13 @@ int decode_layout(int B, int N, int H, int W, int HH, int WW, DecodeScratch* s, 
     return (float*)p;
   };
   float* imf = take(sizeof(float) * 2 * B * qs * 64);
+  float* iml = take(sizeof(float) * 2 * B * qs * 64);
   float* am = take(sizeof(float) * B * qs * 128);
   float* as = take(sizeof(float) * B * qs * 4);
   float* ax = take(sizeof(float) * B * qs);
   float* wp = take(sizeof(float) * WeightPack::total);
   float* wi = take(tc_image_bytes());
-  if (s) *s = DecodeScratch{imf, am, as, ax, wp, wi};
+  if (s) *s = DecodeScratch{imf, iml, am, as, ax, wp, wi};
   if (bytes) *bytes = off;
   return 0;
 }
@@ -498,16 +560,21 @@ int decode_simt(const motif_decode_t* a, cudaStream_t st) {
   const size_t smem = 2 * sizeof(ActBuf);
   static bool attr_done = false;
   if (!attr_done) {
-    MOTIF_CUDA(cudaFuncSetAttribute(imnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MOTIF_CUDA(cudaFuncSetAttribute(flow_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MOTIF_CUDA(cudaFuncSetAttribute(synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(imnet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_splat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(synth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(imnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_splat_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOTIF_CUDA(cudaFuncSetAttribute(synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int tiles = ceil_div(qs, kThreads);
+  const bool ens = a->local_ensemble != 0;
   if (a->n_begin == a->n_end) return 0;
   {
     ProfScope prof("imnet_kernel", st);
-    imnet_kernel<<<dim3(tiles, 2 * g.B), kThreads, smem, st>>>(g, a->feat, sc.wpack, sc.imf);
+    if (ens) imnet_kernel<true><<<dim3(tiles, 2 * g.B), kThreads, smem, st>>>(g, a->feat, sc.wpack, sc.imf, sc.imf_low);
+    else imnet_kernel<false><<<dim3(tiles, 2 * g.B), kThreads, smem, st>>>(g, a->feat, sc.wpack, sc.imf, sc.imf_low);
     MOTIF_LAUNCHED("imnet_kernel");
   }
   MOTIF_CUDA(cudaMemsetAsync(sc.acc_main, 0, sizeof(float) * (size_t)g.B * qs * 128, st));
@@ -519,12 +586,14 @@ int decode_simt(const motif_decode_t* a, cudaStream_t st) {
       const float t = a->target_t[b * g.N + n];
       {
         ProfScope prof("flow_splat_kernel", st);
-        flow_splat_kernel<<<tiles, kThreads, smem, st>>>(g, g.B, g.N, n, t, a->alpha, a->feat, a->flow_feat, sc.imf, sc.wpack, sc, a->flow_out, b);
+        if (ens) flow_splat_kernel<true><<<tiles, kThreads, smem, st>>>(g, g.B, g.N, n, t, a->alpha, a->feat, a->flow_feat, sc.imf, sc.wpack, sc, a->flow_out, b);
+        else flow_splat_kernel<false><<<tiles, kThreads, smem, st>>>(g, g.B, g.N, n, t, a->alpha, a->feat, a->flow_feat, sc.imf, sc.wpack, sc, a->flow_out, b);
         MOTIF_LAUNCHED("flow_splat_kernel");
       }
       {
         ProfScope prof("synth_kernel", st);
-        synth_kernel<<<tiles, kThreads, smem, st>>>(g, g.B, g.N, n, t, a->residual, sc.wpack, sc, a->rgb, a->dbg_synth_in, b);
+        if (ens) synth_kernel<true><<<tiles, kThreads, smem, st>>>(g, g.B, g.N, n, t, a->residual, sc.wpack, sc, a->rgb, a->dbg_synth_in, b);
+        else synth_kernel<false><<<tiles, kThreads, smem, st>>>(g, g.B, g.N, n, t, a->residual, sc.wpack, sc, a->rgb, a->dbg_synth_in, b);
         MOTIF_LAUNCHED("synth_kernel");
       }
     }

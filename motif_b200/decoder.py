@@ -51,10 +51,16 @@ def _key(name: str, layer: int, last: bool, what: str) -> str:
 
 
 class SpaceTimeDecoder:
-    def __init__(self, params: Dict[str, torch.Tensor], device="cuda", precision: str = DEFAULT_PRECISION):
+    def __init__(self, params: Dict[str, torch.Tensor], device="cuda", precision: str = DEFAULT_PRECISION, local_ensemble: bool = False):
+        """``local_ensemble``: the reference's ``LunaTokis.local_ensemble`` flag (``Ours.py:453``; ``False`` as shipped).
+        ``True`` evaluates every query at four shifted latents and blends them by the diagonally swapped area weights
+        (``Ours.py:660-663, 754-764``); implemented by ``precision='fp32'`` only."""
         _lib.load()  # fail loudly when the CUDA library is missing
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {list(PRECISIONS)}")
+        if local_ensemble and precision != "fp32":
+            raise NotImplementedError("local_ensemble=True is implemented by precision='fp32' (the shipped checkpoint runs with it off, Ours.py:453)")
+        self.local_ensemble = bool(local_ensemble)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise NotImplementedError("SpaceTimeDecoder is CUDA-only")
@@ -79,14 +85,14 @@ class SpaceTimeDecoder:
         self._workspace = None
 
     @classmethod
-    def from_state_dict(cls, state_dict, device="cuda", precision=DEFAULT_PRECISION):
+    def from_state_dict(cls, state_dict, device="cuda", precision=DEFAULT_PRECISION, local_ensemble: bool = False):
         """Accepts a full ``LunaTokis`` ``state_dict`` (e.g. ``best.pth``, optional ``module.`` prefix)."""
         clean = {}
         for k, v in state_dict.items():
             k = k[7:] if k.startswith("module.") else k
             if k == "alpha" or k.startswith(HOT_PREFIXES):
                 clean[k] = v
-        return cls(clean, device=device, precision=precision)
+        return cls(clean, device=device, precision=precision, local_ensemble=local_ensemble)
 
     # ------------------------------------------------------------------------------------------
     def _sequences(self, H, W, HH, WW):
@@ -208,6 +214,7 @@ class SpaceTimeDecoder:
             a.dbg_pre0 = pre0.data_ptr() if pre0 is not None else None
             a.n_begin, a.n_end = int(n0), int(n1)
             a.precision = PRECISIONS[precision or self.precision]
+            a.local_ensemble = int(self.local_ensemble)
             rc = lib.motif_decode(ctypes.byref(a), _lib.current_stream_ptr(dev))
         _lib.check(rc, "motif_decode")
         if debug_synth_in:

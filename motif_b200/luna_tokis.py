@@ -92,15 +92,17 @@ def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, tra
     """Same signature and return value as ``LunaTokis.forward`` (``Ours.py:512, 858``)."""
     if self.training or use_GT:
         raise NotImplementedError("motif_b200 implements the inference path (eval(), use_GT=False), as VideoSRBaseModel.test() calls it")
-    for flag, want in (("local_ensemble", False), ("res_liff", False), ("siren", True), ("trans", False), ("warp_to_many", False)):
+    for flag, want in (("res_liff", False), ("siren", True), ("trans", False), ("warp_to_many", False)):
         if getattr(self, flag, want) != want:
             raise NotImplementedError(f"motif_b200 decodes the shipped configuration (setting 5); {flag}={getattr(self, flag)} is not supported")
     with torch.no_grad():
         feat, flow_feat, residual, tt, (HH, WW) = surround(self, x, target_t, scale, iter)
         dec = getattr(self, "_motif_decoder", None)
         sd_version = sum(p._version for p in self.parameters())
-        if dec is None or dec.device != feat.device or self._motif_decoder_version != sd_version:
-            dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, precision=getattr(self, "_motif_precision", "f16x3"))
+        ens = bool(getattr(self, "local_ensemble", False))  # Ours.py:453; the four-latent ensemble runs on the fp32 path
+        if dec is None or dec.device != feat.device or self._motif_decoder_version != sd_version or dec.local_ensemble != ens:
+            dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, local_ensemble=ens,
+                                                   precision="fp32" if ens else getattr(self, "_motif_precision", "f16x3"))
             object.__setattr__(self, "_motif_decoder", dec)
             object.__setattr__(self, "_motif_decoder_version", sd_version)
         rgb, flow_out = dec.decode(feat.float(), flow_feat.float(), residual.float(), tt, (HH, WW))

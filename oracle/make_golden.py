@@ -107,8 +107,9 @@ def _load_hot_params(model, params):
         sd[k].copy_(v)
 
 
-def decoder_case(name, lr_hw, scale, times, batch, use_raft, seed, gain, first_gain, alpha):
+def decoder_case(name, lr_hw, scale, times, batch, use_raft, seed, gain, first_gain, alpha, ensemble=False):
     model = ref_shims.build_reference_model(seed=seed, splat_backend="reference_kernels")
+    model.local_ensemble = ensemble  # Ours.py:453 (False as shipped); True = the four-latent LIIF ensemble of Ours.py:660-663, 758-764
     if not use_raft:
         model.flow_predictor = _SmoothFlow(seed + 7, magnitude=3.0)
     if gain is not None:
@@ -142,11 +143,20 @@ def decoder_cases():
     decoder_case("decoder_x4", (16, 24), 4, [0.125, 0.5, 0.875], 1, False, seed=1, gain=1.0, first_gain=4.0, alpha=-20.0)
     # non-integer scale (round(H*3.5)), two clips: exercises index ties and batch ordering
     decoder_case("decoder_x3p5_b2", (16, 20), 3.5, [0.3, 0.75], 2, False, seed=2, gain=1.0, first_gain=4.0, alpha=-20.0)
+    ensemble_case()
+
+
+def ensemble_case():
+    # the reference's local_ensemble=True branch (four shifted latents, diagonally swapped area weights)
+    decoder_case("decoder_ens_x3", (12, 16), 3, [0.4], 2, False, seed=3, gain=1.0, first_gain=4.0, alpha=-20.0, ensemble=True)
 
 
 if __name__ == "__main__":
     if not build_ref.reference_available():
         raise SystemExit("reference checkout absent: golden vectors can only be regenerated in the build container")
+    if "--ensemble-only" in sys.argv:
+        ensemble_case()
+        raise SystemExit(0)
     splat_cases()
     correlation_cases()
     decoder_cases()

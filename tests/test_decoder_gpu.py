@@ -69,6 +69,35 @@ def test_decoder_vs_reference_golden(case, precision):
     assert p > PSNR_MIN
 
 
+def test_local_ensemble_vs_reference_golden():
+    """LunaTokis.local_ensemble = True (Ours.py:660-663, 754-764; off as shipped): four shifted latents blended by the
+    diagonally swapped area weights.  Golden = the reference's own forward with the flag set (oracle/make_golden.py)."""
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    g = load_golden("decoder_ens_x3")
+    HH, WW = [int(v) for v in g["hr_size"]]
+    dec = SpaceTimeDecoder(hot_params(g), device="cuda", precision="fp32", local_ensemble=True)
+    rgb, flow = dec.decode(g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
+    assert rgb.shape == g["out"].shape and flow.shape == g["flow_out"].shape
+    d_flow = (flow.cpu() - g["flow_out"]).abs().max().item()
+    assert d_flow < FLOW_TOL, d_flow
+    B, N = g["target_t"].shape
+    d_rgb, p, _ = _compare_frames(rgb.cpu(), g["out"], g["flow_out"], HH / g["feat"].shape[-2], B, N)
+    assert d_rgb < TOL, d_rgb
+    assert p > PSNR_MIN
+    # the flag changes the function: the single-latent decode of the same inputs is far from this golden
+    plain, _ = SpaceTimeDecoder(hot_params(g), device="cuda", precision="fp32").decode(
+        g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
+    assert (plain.cpu() - g["out"]).abs().max().item() > 5e-3
+
+
+def test_local_ensemble_needs_fp32():
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    with pytest.raises(NotImplementedError):
+        SpaceTimeDecoder(decoder_ref.random_params(0), device="cuda", precision="f16x3", local_ensemble=True)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 def test_decoder_stages_vs_oracle(precision):
     """Seeded O(1)-scaled weights; compares the blended splat + reliability features (the synth_net input,

@@ -60,6 +60,17 @@ def test_decoder_oracle_reproduces_reference_forward(case):
     assert (flow - g["flow_out"]).abs().max().item() < 2e-5
 
 
+def test_decoder_oracle_local_ensemble_reproduces_reference_forward():
+    """The oracle's local_ensemble=True branch against the reference's own forward with the flag set."""
+    g = load_golden("decoder_ens_x3")
+    HH, WW = [int(v) for v in g["hr_size"]]
+    rgb, flow = decoder_ref.decode(g["feat"], g["flow_feat"], g["residual"], g["target_t"], HH, WW, hot_params(g), local_ensemble=True)
+    assert (rgb - g["out"]).abs().max().item() < 2e-5
+    assert (flow - g["flow_out"]).abs().max().item() < 2e-5
+    plain, _ = decoder_ref.decode(g["feat"], g["flow_feat"], g["residual"], g["target_t"], HH, WW, hot_params(g))
+    assert (plain - g["out"]).abs().max().item() > 5e-3  # the fixture does exercise the flag
+
+
 def test_hr_size_rounding_matches_reference_rule():
     g = load_golden("decoder_x3p5_b2")
     H, W = g["feat"].shape[-2:]
