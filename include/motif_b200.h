@@ -85,6 +85,17 @@ int motif_splat_count_fwd(const float* flow, float* out, int n, int h, int w, vo
 int motif_corr_fwd(const float* first, const float* second, float* out, int b, int c, int h, int w, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Reliability maps + flow-encoder input (the step upstream of the decoder).  Replaces
+ * models/modules/Ours.py:562-578 (psi_photo / psi_flow / psi_var through BackWarp, :892-923, and the 3x3 gaussian
+ * conv3d with reflect padding) and :613-637 (the tensor handed to flow_process; trans=False, input_Z=True).
+ *   fr0, fr1 [B, 3, H, W]   the two LR frames           flow [4B, 2, H, W]  LR flows of the pairs 00, 01, 10, 11
+ *   g_filter [9]            LunaTokis.g_filter          out  [2B, 14, H, W] per reference r and pair j = 0, 1:
+ *                           [flow / 20 (2) | psi_photo, psi_flow / 10, psi_var | durations / 8 (2)]
+ * ---------------------------------------------------------------------------------- */
+int motif_flow_front(const float* fr0, const float* fr1, const float* flow, const float* g_filter, float* out, int B, int H, int W,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Space-time local implicit decoder.  Replaces models/modules/Ours.py:659-858 (LunaTokis.forward
  * from make_coord to the clamp) with SIREN MLPs of models/modules/SIREN.py:44-45, 76-79.
  * ---------------------------------------------------------------------------------- */

@@ -28,6 +28,7 @@ EXPORTS = [
     "motif_splat_max_fwd",
     "motif_splat_count_fwd",
     "motif_corr_fwd",
+    "motif_flow_front",
     "motif_query_geometry",
     "motif_pack_latents",
     "motif_decode_workspace_bytes",
@@ -101,6 +102,8 @@ def _declare(lib):
     lib.motif_splat_count_fwd.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_corr_fwd.restype = c_int
     lib.motif_corr_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
+    lib.motif_flow_front.restype = c_int
+    lib.motif_flow_front.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_query_geometry.restype = c_int
     lib.motif_query_geometry.argtypes = [POINTER(GeomT), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.motif_pack_latents.restype = c_int

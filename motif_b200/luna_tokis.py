@@ -9,8 +9,9 @@
 replaces ``forward`` by ``forward_b200``, which
 
 * runs the surround exactly as the reference does, through the instance's own sub-modules
-  (RAFT on the four frame pairs, the psi reliability maps, ``ZSM_encoder``, ``flow_process``;
-  ``Ours.py:512-638``) -- glue re-stated here because the reference's ``forward`` is monolithic;
+  (RAFT on the four frame pairs, ``ZSM_encoder``, ``flow_process``; ``Ours.py:512-638``) -- glue re-stated here
+  because the reference's ``forward`` is monolithic; on a CUDA device the psi reliability maps and the assembly of the
+  ``flow_process`` input (``Ours.py:562-578, 613-637``) run as one kernel (``motif_b200.flow_front``);
 * hands the three LR latents to ``SpaceTimeDecoder`` (``Ours.py:659-858`` on sm_100a) and returns the
   reference's triple ``(clamp(out) [N,B,3,HH,WW], flow / 20 / (HH/H), flow_GT)`` (``Ours.py:858``).
 
@@ -29,6 +30,7 @@ import torch.nn.functional as F
 from torch.nn.functional import interpolate
 
 from .decoder import SpaceTimeDecoder, hr_size_from_scale
+from .flow_front import flow_front
 from .softsplat_count_cp import Softsplat_Count
 from .softsplat_cp import Softsplat
 from .softsplat_max_cp import Softsplat_Max
@@ -56,6 +58,15 @@ def surround(self, x, target_t, scale, iter=12):
         flow[3] *= 0.0
         flow = flow.reshape(4 * B, 2, H, W)
 
+        fused_front = flow.is_cuda and not (self.trans or not self.input_Z)
+        if fused_front:  # Ours.py:562-578 + 613-637 in one kernel (motif_flow_front)
+            front_in = flow_front(fr0.float(), fr1.float(), flow.float(), self.g_filter)
+    if fused_front:
+        feat = self.encoder(torch.stack([fr0, fr1], 1), None)
+        residual = feat[:, feat.shape[1] // 2].reshape(B, -1, H, W)
+        feat = torch.cat((feat[:, feat.shape[1] // 2 - 1], feat[:, feat.shape[1] // 2 + 1]), 0)
+        return feat, self.flow_process(front_in), residual, target_t, (HH, WW)
+    with torch.no_grad():
         # reliability maps psi_photo, psi_flow, psi_var (Ours.py:562-578)
         warped, _ = self.bwarp(torch.cat([fr0, fr1, fr0, fr1], dim=0), flow)
         psi_photo = F.l1_loss(input=torch.cat([fr0, fr0, fr1, fr1], dim=0), target=warped, reduction="none").mean(1)

@@ -146,6 +146,22 @@ def decoder_cases():
     ensemble_case()
 
 
+def front_cases():
+    """Reliability-map front end (Ours.py:562-578, 613-637): LR frames, the HR flows RAFT (or its stand-in) returned and
+    the tensor the reference handed to flow_process, captured while its unmodified forward ran."""
+    for name, lr_hw, scale, batch, use_raft, seed in (("front_raft", (32, 48), 4, 1, True, 5), ("front_smooth_b2", (20, 28), 3, 2, False, 6)):
+        model = ref_shims.build_reference_model(seed=seed, splat_backend="reference_kernels")
+        if not use_raft:
+            model.flow_predictor = _SmoothFlow(seed + 7, magnitude=6.0)
+        torch.manual_seed(seed + 1)
+        h, w = lr_hw
+        low = torch.rand(batch, 2, 3, max(h // 4, 2), max(w // 4, 2))
+        x = torch.nn.functional.interpolate(low.view(batch * 2, 3, *low.shape[-2:]), size=(h, w), mode="bilinear").view(batch, 2, 3, h, w)
+        x = (x + 0.05 * torch.rand(batch, 2, 3, h, w)).clamp(0, 1)
+        r = ref_shims.run_reference_forward(model, x, [torch.full((batch, 1), 0.5)], scale)
+        _save(name, x=x, flow_hr=r["flow_hr"], g_filter=model.g_filter.detach().reshape(3, 3), flow_process_in=r["flow_process_in"])
+
+
 def ensemble_case():
     # the reference's local_ensemble=True branch (four shifted latents, diagonally swapped area weights)
     decoder_case("decoder_ens_x3", (12, 16), 3, [0.4], 2, False, seed=3, gain=1.0, first_gain=4.0, alpha=-20.0, ensemble=True)
@@ -157,6 +173,10 @@ if __name__ == "__main__":
     if "--ensemble-only" in sys.argv:
         ensemble_case()
         raise SystemExit(0)
+    if "--front-only" in sys.argv:
+        front_cases()
+        raise SystemExit(0)
     splat_cases()
     correlation_cases()
     decoder_cases()
+    front_cases()

@@ -168,18 +168,25 @@ def run_reference_forward(model, x, target_t, scale, iters=4):
 
     def fp_hook(_m, _i, out):
         captured["flow_feat"] = out.detach().clone()
+        captured["flow_process_in"] = _i[0].detach().clone()  # [2B,14,H,W]: flow / 20, psi maps, durations (Ours.py:614-637)
+
+    def raft_hook(_m, _i, out):
+        captured["flow_hr"] = out[-1].detach().clone()  # [4B,2,HH,WW] (Ours.py:545-546)
 
     h1 = model.encoder.register_forward_hook(enc_hook)
     h2 = model.flow_process.register_forward_hook(fp_hook)
+    h3 = model.flow_predictor.register_forward_hook(raft_hook)
     try:
         with torch.no_grad(), cpu_cuda_aliases():
             out, flow, flow_gt = model(x, None, target_t, scale, use_GT=False, iter=iters)
     finally:
         h1.remove()
         h2.remove()
+        h3.remove()
     enc = captured["encoder_out"]  # [B,3,64,H,W]
     B = enc.shape[0]
     H, W = enc.shape[-2:]
     residual = enc[:, enc.shape[1] // 2].reshape(B, -1, H, W)
     feat = torch.cat((enc[:, enc.shape[1] // 2 - 1], enc[:, enc.shape[1] // 2 + 1]), 0)
-    return {"out": out, "flow_out": flow, "feat": feat, "flow_feat": captured["flow_feat"], "residual": residual}
+    return {"out": out, "flow_out": flow, "feat": feat, "flow_feat": captured["flow_feat"], "residual": residual,
+            "flow_process_in": captured["flow_process_in"], "flow_hr": captured["flow_hr"]}

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from conftest import hot_params, load_golden
-from oracle import build_ref, correlation_ref, decoder_ref, softsplat_ref
+from oracle import build_ref, correlation_ref, decoder_ref, flow_front_ref, softsplat_ref
 
 SPLAT_CASES = ["splat_s05", "splat_s4", "splat_s32"]
 
@@ -69,6 +69,18 @@ def test_decoder_oracle_local_ensemble_reproduces_reference_forward():
     assert (flow - g["flow_out"]).abs().max().item() < 2e-5
     plain, _ = decoder_ref.decode(g["feat"], g["flow_feat"], g["residual"], g["target_t"], HH, WW, hot_params(g))
     assert (plain - g["out"]).abs().max().item() > 5e-3  # the fixture does exercise the flag
+
+
+@pytest.mark.parametrize("case", ["front_raft", "front_smooth_b2"])
+def test_flow_front_oracle_reproduces_reference_flow_process_input(case):
+    """Ours.py:562-578, 613-637: the tensor the reference handed to flow_process while its own forward ran."""
+    g = load_golden(case)
+    x = g["x"]
+    B, H, W = x.shape[0], x.shape[-2], x.shape[-1]
+    flow = flow_front_ref.lr_flow_from_hr(g["flow_hr"], B, H, W)
+    out = flow_front_ref.flow_front(x[:, 0], x[:, 1], flow, g["g_filter"])
+    assert out.shape == g["flow_process_in"].shape
+    assert (out - g["flow_process_in"]).abs().max().item() < 1e-6
 
 
 def test_hr_size_rounding_matches_reference_rule():
