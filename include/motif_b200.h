@@ -154,6 +154,9 @@ typedef struct {
   int local_ensemble;  /* LunaTokis.local_ensemble (Ours.py:453, 660-663, 754-764): 0 as shipped = one nearest latent;
                         * 1 = the four shifted latents blended by diagonally swapped area weights.  Implemented by
                         * MOTIF_PRECISION_FP32 only (other precisions return MOTIF_E_UNSUPPORTED).       */
+  int weights_ready;   /* 1: `workspace` still holds the weight images a previous motif_decode wrote for THESE weights at THIS
+                        * precision (same workspace pointer, nothing else wrote to it): the per-call repacking is skipped.
+                        * Honoured by MOTIF_PRECISION_F16X3; 0 is always safe.                                          */
 } motif_decode_t;
 
 /* MLP arithmetic.  F16X3 (default of the Python mirror): tcgen05 kind::f16, every fp32 operand split into two

@@ -75,6 +75,7 @@ class DecodeT(Structure):
         ("n_begin", c_int), ("n_end", c_int),
         ("precision", c_int),
         ("local_ensemble", c_int),
+        ("weights_ready", c_int),
     ]
 
 

@@ -1485,10 +1485,9 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) {
+// Weight-dependent images (clip-invariant): skipped when the caller vouches that the workspace still holds them.
+static int prepare_weights(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) {
   using Wp = WeightPack;
-  const motif_geom_t& g = a->geom;
-  const int P = g.H * g.W, B = g.B;
   if (int rc = pack_weights(a, sc.wpack, st)) return rc;
   fold_kernel<<<64, 256, 0, st>>>(sc.wpack, sc.fold);
   MOTIF_LAUNCHED("fold_kernel");
@@ -1519,7 +1518,28 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
 #ifndef MOTIF_OUT3_SMEM
   out3_consts_kernel<<<1, 256, 0, st>>>(sc.wpack, sc.out3c);
   MOTIF_LAUNCHED("out3_consts_kernel");
-  MOTIF_CUDA(cudaMemcpyToSymbolAsync(c_out3, sc.out3c, sizeof(c_out3), 0, cudaMemcpyDeviceToDevice, st));
+#endif
+  return 0;
+}
+
+static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) {
+  using Wp = WeightPack;
+  const motif_geom_t& g = a->geom;
+  const int P = g.H * g.W, B = g.B;
+  if (!a->weights_ready)
+    if (int rc = prepare_weights(a, sc, st)) return rc;
+#ifndef MOTIF_OUT3_SMEM
+  {
+    // The constant bank is per device, not per workspace: re-upload when another workspace's constants are in it.
+    // (Two decoders with DIFFERENT weights decoding concurrently on two streams of one device would race on it.)
+    static const void* owner[64] = {nullptr};
+    int dev = 0;
+    MOTIF_CUDA(cudaGetDevice(&dev));
+    if (!a->weights_ready || owner[dev & 63] != (const void*)sc.out3c) {
+      MOTIF_CUDA(cudaMemcpyToSymbolAsync(c_out3, sc.out3c, sizeof(c_out3), 0, cudaMemcpyDeviceToDevice, st));
+      owner[dev & 63] = (const void*)sc.out3c;
+    }
+  }
 #endif
   // LR tables
   LrJobs lj;

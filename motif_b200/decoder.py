@@ -83,6 +83,7 @@ class SpaceTimeDecoder:
         self.alpha = float(params["alpha"].detach().float().reshape(-1)[0].item())
         self._seq_cache = {}
         self._workspace = None
+        self._ws_weights_key = None
 
     @classmethod
     def from_state_dict(cls, state_dict, device="cuda", precision=DEFAULT_PRECISION, local_ensemble: bool = False):
@@ -215,8 +216,13 @@ class SpaceTimeDecoder:
             a.n_begin, a.n_end = int(n0), int(n1)
             a.precision = PRECISIONS[precision or self.precision]
             a.local_ensemble = int(self.local_ensemble)
+            # the weight images in the workspace are clip-invariant: repacked only when the workspace or the arithmetic changed
+            ws_key = (ws.data_ptr(), a.precision)
+            a.weights_ready = int(self._ws_weights_key == ws_key)
+            self._ws_weights_key = None  # a failing call leaves the workspace in an unknown state
             rc = lib.motif_decode(ctypes.byref(a), _lib.current_stream_ptr(dev))
         _lib.check(rc, "motif_decode")
+        self._ws_weights_key = ws_key
         if debug_synth_in:
             return rgb, flow_out, dbg
         if debug_pre0:

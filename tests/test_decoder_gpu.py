@@ -91,6 +91,28 @@ def test_local_ensemble_vs_reference_golden():
     assert (plain.cpu() - g["out"]).abs().max().item() > 5e-3
 
 
+def test_weight_images_are_reused_and_two_decoders_do_not_mix():
+    """Second call on the same workspace skips the weight repacking (motif_decode_t.weights_ready); a second decoder
+    with other weights in between re-uploads its own output-layer constants (the constant bank is per device)."""
+    from motif_b200 import synthetic
+
+    B, H, W, HH, WW = 1, 12, 16, 48, 64
+    feat, ff, res = [t.cuda() for t in synthetic.synthetic_latents(B, H, W, seed=3)]
+    tt = torch.tensor([[0.25, 0.75]])
+    dec_a = _decoder(synthetic.synthetic_params(seed=3), "f16x3")
+    dec_b = _decoder(synthetic.synthetic_params(seed=4), "f16x3")
+    a1, fa1 = dec_a.decode(feat, ff, res, tt, (HH, WW))
+    b1, _ = dec_b.decode(feat, ff, res, tt, (HH, WW))
+    a2, fa2 = dec_a.decode(feat, ff, res, tt, (HH, WW))      # weights_ready = 1, constants of dec_b in the bank
+    b2, _ = dec_b.decode(feat, ff, res, tt, (HH, WW))
+    a3, _ = dec_a.decode(feat, ff, res, tt, (HH, WW), precision="fp32")   # another layout overwrites the images
+    a4, _ = dec_a.decode(feat, ff, res, tt, (HH, WW))                     # ... so they are rebuilt
+    assert torch.equal(fa1, fa2)
+    assert (a1 - a2).abs().max().item() < 1e-6 and (b1 - b2).abs().max().item() < 1e-6 and (a1 - a4).abs().max().item() < 1e-6
+    assert (a1 - b1).abs().max().item() > 1e-3
+    assert (a1 - a3).abs().max().item() < 1e-2  # same function in exact fp32 (unstable-count pixels aside)
+
+
 def test_local_ensemble_needs_fp32():
     from motif_b200.decoder import SpaceTimeDecoder
 

@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 # kernel symbol -> the name bench.py's per-kernel timers use
-ALIAS = {"flow_bin_q_kernel": "flow_bin_f16_kernel", "synth_q_kernel": "synth_f16_kernel"}
+ALIAS = {"flow_bin_q_kernel": "flow_bin_f16_kernel", "synth_q_kernel": "synth_f16_kernel", "splat_gather_tiled_kernel": "splat_gather_kernel"}
 
 out = {}
 for rep in sys.argv[1:]:

@@ -31,7 +31,7 @@ print("decode ok", tuple(rgb.shape), float(rgb.mean()))
 if a.splat:
     torch.manual_seed(0)
     x = torch.randn(1, 130, HH, WW, device=dev)
-    low = torch.randn(1, 2, HH // 16, WW // 16, device=dev) * 6
+    low = torch.randn(1, 2, HH // 64, WW // 64, device=dev) * 6  # the smooth field bench.py's roofline_splat uses
     fl = torch.nn.functional.interpolate(low, size=(HH, WW), mode="bilinear", align_corners=False).contiguous()
     z = -torch.rand(1, 1, HH, WW, device=dev)
     for _ in range(a.reps):
