@@ -311,15 +311,20 @@ __global__ void __launch_bounds__(256) splat_gather_kernel(const float* __restri
 // not fit (strongly diverging flow) and planes whose rows are not 16-byte aligned take the direct path above.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 8;    // destination tile
-#ifndef MOTIF_SPLAT_RW
-#define MOTIF_SPLAT_RW 64
-#define MOTIF_SPLAT_RH 16
+// Staging buffer: kBufFloats floats of dynamic shared memory per CTA (two CTAs per SM), cut into stages of kCH channel
+// planes.  A plane holds the tile's actual source window (rw x rh floats, rw a multiple of 4, at most 256 16-byte
+// columns so that every thread copies one) plus a zero word -- NOT a worst-case 64 x 16 rectangle: a smooth flow needs
+// ~40 x 11, so the same memory holds seven chunks instead of three and five to six of them are in flight.  (With three
+// stages a chunk took one memory round trip, ~1.5 us: two chunks in flight cannot cover the latency.)
+#ifndef MOTIF_SPLAT_BUF_KB
+#define MOTIF_SPLAT_BUF_KB 98
 #endif
-constexpr int kRW = MOTIF_SPLAT_RW, kRH = MOTIF_SPLAT_RH;   // staged source window (floats x rows): at most 256 16-byte columns, one per thread
-static_assert((kRW / 4) * kRH <= 256 && kRW % 4 == 0, "one 16-byte column of the window per thread");
-constexpr int kPlane = kRH * kRW + 4; // floats per staged channel plane: the window + a zero word (16-byte padded)
-constexpr int kStages = 3;          // staged chunks: one being read, kStages - 1 in flight (>= 3: one barrier per chunk suffices)
-constexpr int kTiledSmem = kStages * 8 * kPlane * (int)sizeof(float);
+constexpr int kBufFloats = MOTIF_SPLAT_BUF_KB * 256;
+constexpr int kMaxCols16 = 256;     // 16-byte columns of a window: one per thread
+constexpr int kTiledSmem = kBufFloats * (int)sizeof(float);
+constexpr int kPlaneLarge = kMaxCols16 * 4 + 4, kDepthLarge = kBufFloats / (8 * kPlaneLarge);  // any window: 3 stages in 98 KB
+constexpr int kPlaneSmall = 512 + 4, kDepthSmall = kBufFloats / (8 * kPlaneSmall);              // windows <= 512 floats: 6 stages
+static_assert(kDepthLarge >= 3 && kDepthSmall >= 3, "at least three stages (one barrier per chunk)");
 constexpr int kCH = 8;              // channels per stage
 
 typedef unsigned long long f32x2;
@@ -349,17 +354,17 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // channels [0, nch) of one staged chunk, K slots per destination, two channels per instruction.  Slots past the
 // list length point at the zero word that follows every staged plane and carry weight 0: they add +0 (exact) without a
 // predicate, and can never pick up a non-finite input the way a real window element could.
-template <int MODE, int K, bool FULL>
+template <int MODE, int K, bool FULL, int PLANE>
 __device__ __forceinline__ void tile_channels(const float* __restrict__ stage, float* __restrict__ optr, int nch, size_t hw,
                                               const int (&off)[kBinSlots], const float (&wt)[kBinSlots], const float (&m)[kBinSlots], bool store) {
 #pragma unroll
   for (int cp = 0; cp < kCH / 2; ++cp) {
     if (!FULL && 2 * cp >= nch) break;
-    const float* p0 = stage + (2 * cp) * kPlane;
+    const float* p0 = stage + (2 * cp) * PLANE;
     float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      f32x2 t = pack2(p0[off[k]], p0[off[k] + kPlane]);
+      f32x2 t = pack2(p0[off[k]], p0[off[k] + PLANE]);
       if (MODE >= MOTIF_SPLAT_LINEAR) t = fmul2(t, pack2(m[k], m[k]));
       t = fmul2(t, pack2(wt[k], wt[k]));
       // scalar adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding instead of the reference's two)
@@ -376,15 +381,54 @@ __device__ __forceinline__ void tile_channels(const float* __restrict__ stage, f
   }
 }
 
-template <int MODE>
+// The chunk pipeline of one tile with D stages: chunk q + D - 1 is requested when chunk q is consumed; one barrier per
+// chunk (it publishes chunk q and retires chunk q - 1, whose stage is the one refilled).
+template <int MODE, int D, int PLANE>
+__device__ __forceinline__ void tile_pipeline(float* __restrict__ buf, int c, size_t hw, const float* __restrict__ csrc, int cdst, bool copier,
+                                              float* __restrict__ optr, int wmax, const int (&off)[kBinSlots], const float (&wt)[kBinSlots],
+                                              const float (&m)[kBinSlots], bool live) {
+  const int n_chunks = (c + kCH - 1) / kCH;
+  constexpr int chunk = kCH * PLANE;
+  static_assert(D * chunk <= kBufFloats, "stages do not fit the staging buffer");
+  auto stage_in = [&](int q) {
+    if (copier) {
+      const int c0 = q * kCH, nch = min(kCH, c - c0);
+      float* dst = buf + (q % D) * chunk + cdst;
+      const float* sp = csrc + (size_t)c0 * hw;
+      for (int ch = 0; ch < nch; ++ch) cp_async16(dst + ch * PLANE, sp + (size_t)ch * hw);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int q = 0; q < D - 1; ++q) {
+    if (q < n_chunks) stage_in(q);
+    else cp_async_commit();
+  }
+  for (int q = 0; q < n_chunks; ++q) {
+    cp_async_wait<D - 2>();  // chunk q has landed (this thread's copies; the barrier publishes everyone's)
+    __syncthreads();         // ... and every thread is done with chunk q - 1, whose stage is refilled next
+    if (q + D - 1 < n_chunks) stage_in(q + D - 1);
+    else cp_async_commit();
+    const int c0 = q * kCH, nch = min(kCH, c - c0);
+    float* o = optr + (size_t)c0 * hw;
+    const float* st = buf + (q % D) * chunk;
+    if (nch == kCH) {
+      if (wmax <= 4) tile_channels<MODE, 4, true, PLANE>(st, o, nch, hw, off, wt, m, live);
+      else if (wmax <= 6) tile_channels<MODE, 6, true, PLANE>(st, o, nch, hw, off, wt, m, live);
+      else tile_channels<MODE, 8, true, PLANE>(st, o, nch, hw, off, wt, m, live);
+    } else {
+      tile_channels<MODE, 8, false, PLANE>(st, o, nch, hw, off, wt, m, live);
+    }
+  }
+}
+
 #ifndef MOTIF_SPLAT_CTAS
 #define MOTIF_SPLAT_CTAS 2
 #endif
+template <int MODE>
 __global__ void __launch_bounds__(256, MOTIF_SPLAT_CTAS) splat_gather_tiled_kernel(const float* __restrict__ in, const float* __restrict__ metric,
-                                                                 float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
-  extern __shared__ __align__(16) float buf_raw[];  // [kStages][kCH][kPlane]
-  float(*buf)[kCH * kPlane] = reinterpret_cast<float(*)[kCH * kPlane]>(buf_raw);
-  if (threadIdx.x < kStages * kCH) buf_raw[threadIdx.x * kPlane + kRH * kRW] = 0.0f;  // the zero word of every plane
+                                                                    float* __restrict__ out, SplatWorkspace ws, int n, int c, int h, int w) {
+  extern __shared__ __align__(16) float buf[];  // [stages][kCH][plane], plane = window + zero word
   __shared__ int s_box[4];  // min x, min y, max x, max y of the sources this tile gathers from
   const int hw = h * w;
   const size_t total = (size_t)n * hw;
@@ -416,59 +460,36 @@ __global__ void __launch_bounds__(256, MOTIF_SPLAT_CTAS) splat_gather_tiled_kern
   __syncthreads();
   const int x0a = s_box[0] & ~3, y0 = s_box[1];
   const int rw4 = (((s_box[2] + 4) & ~3) - x0a) >> 2, rh = s_box[3] - y0 + 1;  // window: rw4 16-byte columns x rh rows
-  const float* plane = in + (size_t)b * c * hw;
+  const int rw = 4 * rw4;
+  const float* plane_in = in + (size_t)b * c * hw;
   float* optr = out + (size_t)b * c_out * hw + d;
   const bool empty = s_box[2] < 0;
-  if (!empty && (rw4 * 4 > kRW || rh > kRH)) {  // window too large for the stage: direct gathers (block-uniform branch)
-    if (wmax <= 4) gather_channels<MODE, 4>(plane, optr, c, hw, cnt, src, wt, m, live);
-    else if (wmax <= 6) gather_channels<MODE, 6>(plane, optr, c, hw, cnt, src, wt, m, live);
-    else gather_channels<MODE, 8>(plane, optr, c, hw, cnt, src, wt, m, live);
+  const int n16 = empty ? 0 : rw4 * rh;  // 16-byte columns of the window: one per thread
+  if (n16 > kMaxCols16) {  // window too large for the stage: direct gathers (block-uniform branch)
+    if (wmax <= 4) gather_channels<MODE, 4>(plane_in, optr, c, hw, cnt, src, wt, m, live);
+    else if (wmax <= 6) gather_channels<MODE, 6>(plane_in, optr, c, hw, cnt, src, wt, m, live);
+    else gather_channels<MODE, 8>(plane_in, optr, c, hw, cnt, src, wt, m, live);
   } else {
+    // plane capacity (compile-time, so that the channel planes sit at immediate offsets): small windows get the deep pipeline
+    const bool small = n16 * 4 <= kPlaneSmall - 4;
+    const int zero_at = small ? kPlaneSmall - 4 : kPlaneLarge - 4;
     int off[kBinSlots];
 #pragma unroll
     for (int k = 0; k < kBinSlots; ++k) {
       const bool on = k < cnt;
-      off[k] = on ? (sy[k] - y0) * kRW + (sx[k] - x0a) : kRH * kRW;
+      off[k] = on ? (sy[k] - y0) * rw + (sx[k] - x0a) : zero_at;  // dead slots read the zero word behind the window
       wt[k] = on ? wt[k] : 0.0f;
       m[k] = on ? m[k] : 1.0f;
     }
+    // the zero word of every plane the pipeline will use (cp.async never writes it; published by the first barrier)
+    if ((int)threadIdx.x < (small ? kDepthSmall : kDepthLarge) * kCH) buf[threadIdx.x * (small ? kPlaneSmall : kPlaneLarge) + zero_at] = 0.0f;
     // this thread's 16-byte column of the window (same for every channel)
-    const int n16 = empty ? 0 : rw4 * rh;
     const bool copier = (int)threadIdx.x < n16;
     const int crow = copier ? (int)threadIdx.x / rw4 : 0, ccol = copier ? (int)threadIdx.x - crow * rw4 : 0;
-    const float* csrc = plane + (size_t)(y0 + crow) * w + x0a + 4 * ccol;
-    const int cdst = crow * kRW + 4 * ccol;
-    const int n_chunks = (c + kCH - 1) / kCH;
-    auto stage_in = [&](int q) {
-      if (copier) {
-        const int c0 = q * kCH, nch = min(kCH, c - c0);
-        float* dst = &buf[q % kStages][cdst];
-        const float* sp = csrc + (size_t)c0 * hw;
-        for (int ch = 0; ch < nch; ++ch) cp_async16(dst + ch * kPlane, sp + (size_t)ch * hw);
-      }
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int q = 0; q < kStages - 1; ++q) {
-      if (q < n_chunks) stage_in(q);
-      else cp_async_commit();
-    }
-    for (int q = 0; q < n_chunks; ++q) {
-      cp_async_wait<kStages - 2>();  // chunk q has landed (this thread's copies; the barrier publishes everyone's)
-      __syncthreads();               // ... and every thread is done with chunk q - 1, whose stage is refilled next
-      if (q + kStages - 1 < n_chunks) stage_in(q + kStages - 1);
-      else cp_async_commit();
-      const int c0 = q * kCH, nch = min(kCH, c - c0);
-      float* o = optr + (size_t)c0 * hw;
-      const float* st = buf[q % kStages];
-      if (nch == kCH) {
-        if (wmax <= 4) tile_channels<MODE, 4, true>(st, o, nch, hw, off, wt, m, live);
-        else if (wmax <= 6) tile_channels<MODE, 6, true>(st, o, nch, hw, off, wt, m, live);
-        else tile_channels<MODE, 8, true>(st, o, nch, hw, off, wt, m, live);
-      } else {
-        tile_channels<MODE, 8, false>(st, o, nch, hw, off, wt, m, live);
-      }
-    }
+    const float* csrc = plane_in + (size_t)(y0 + crow) * w + x0a + 4 * ccol;
+    const int cdst = crow * rw + 4 * ccol;
+    if (small) tile_pipeline<MODE, kDepthSmall, kPlaneSmall>(buf, c, hw, csrc, cdst, copier, optr, wmax, off, wt, m, live);
+    else tile_pipeline<MODE, kDepthLarge, kPlaneLarge>(buf, c, hw, csrc, cdst, copier, optr, wmax, off, wt, m, live);
   }
   if (MODE != MOTIF_SPLAT_SUMMATION && live) {
     float acc = 0.0f;
