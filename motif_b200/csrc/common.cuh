@@ -41,6 +41,15 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (dynamic shared memory size, carve-out) belong to the DEVICE the kernel is loaded on: a process
+// that drives several GPUs (the reference wraps the model in DataParallel, VideoSR_base_model.py:36) must set them once
+// per device, not once per process.  Returns the slot of the current device in a caller-owned `done[64]` table.
+inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & 63;
+}
+
 // Optional per-kernel timing (motif_prof_*): CUDA events recorded on the launch stream around a kernel.
 struct ProfScope {
   int slot;

@@ -223,7 +223,8 @@ extern "C" int motif_corr_fwd(const float* first, const float* second, float* ou
   int ksplit = 1;
   while (ksplit < 8 && tiles * ksplit * 2 <= 148 * 3 && ceil_div(c, kCC) >= ksplit * 2 * 4) ksplit *= 2;  // three CTAs fit per SM; >= 4 chunks each
   MOTIF_REQUIRE((long long)b * ksplit <= 65535, "corr: batch too large");
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};
+  bool& attr_done = attr_done_dev[current_device_slot()];
   if (!attr_done) {
     MOTIF_CUDA(cudaFuncSetAttribute(corr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmemBytes));
     MOTIF_CUDA(cudaFuncSetAttribute(corr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCorrSmemBytes));

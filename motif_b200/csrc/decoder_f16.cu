@@ -1608,7 +1608,8 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   const size_t qs = (size_t)g.HH * g.WW;
   const int smem_fq = (int)sizeof(QSmemF) + 1024, smem_sq = (int)sizeof(QSmemS) + 1024, smem_i = (int)sizeof(SmemI) + 1024;
   const int g_blocks = ceil_div(g.WW, kGW) * ceil_div(g.HH, kGH);
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};
+  bool& attr_done = attr_done_dev[current_device_slot()];
   static int n_sm = 148;
   if (!attr_done) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));

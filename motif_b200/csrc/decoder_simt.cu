@@ -558,7 +558,8 @@ int decode_simt(const motif_decode_t* a, cudaStream_t st) {
   if (int rc = pack_weights(a, sc.wpack, st)) return rc;
   const int qs = g.HH * g.WW;
   const size_t smem = 2 * sizeof(ActBuf);
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};
+  bool& attr_done = attr_done_dev[current_device_slot()];
   if (!attr_done) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MOTIF_CUDA(cudaFuncSetAttribute(flow_splat_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -815,7 +815,8 @@ int decode_tc(const motif_decode_t* a, cudaStream_t st) {
   if (int rc = pack_images(sc.wpack, sc.wimg, st)) return rc;
   const int qs = g.HH * g.WW;
   const int smem = (int)sizeof(TcSmem) + 1024;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {false};
+  bool& attr_done = attr_done_dev[current_device_slot()];
   static int n_sm = 148;
   if (!attr_done) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -583,7 +583,8 @@ static int launch_gather(const float* in, const float* metric, float* out, const
   ProfScope prof("splat_gather_kernel", st);
   if (tiled) {
     dim3 grid(ceil_div(w, kTW) * ceil_div(h, kTH), n);
-    static bool attr_done = false;  // per MODE instantiation
+    static bool attr_done_dev[64] = {false};  // per MODE instantiation
+  bool& attr_done = attr_done_dev[current_device_slot()];
     if (!attr_done) {
       MOTIF_CUDA(cudaFuncSetAttribute(splat_gather_tiled_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmem));
       attr_done = true;

@@ -246,6 +246,57 @@ def test_adobe_full_size_properties(precision):
     assert torch.quantile(d.flatten()[::7].float(), 0.999).item() < TOL
 
 
+@pytest.mark.parametrize("workload,n_take", [("adobe240_x3p5_t12", 2), ("uhd4k_x4_t8", 1)])
+def test_other_baseline_configs_full_size(workload, n_take):
+    """BASELINE configs 3 (x3.5 space, round(H * 3.5); x12 time) and 4 (4K output) at FULL size: the f16x3 path against
+    the exact-fp32 CUDA-core path on the device for the first timestamps, finite / clamped output for all decoded ones."""
+    from motif_b200 import synthetic
+
+    H, W, HH, WW, times = synthetic.WORKLOADS[workload]
+    feat, ff, res = [t.cuda() for t in synthetic.synthetic_latents(1, H, W, seed=5)]
+    params = decoder_ref.random_params(seed=2, **decoder_ref.REALISTIC)
+    n_f16 = min(len(times), 3 if HH > 2000 else len(times))
+    tt = torch.tensor([times[:n_f16]])
+    a, fa = _decoder(params, "f16x3").decode(feat, ff, res, tt, (HH, WW))
+    assert a.shape == (n_f16, 1, 3, HH, WW) and torch.isfinite(a).all()
+    assert a.min().item() >= 0.0 and a.max().item() <= 1.0
+    b, fb = _decoder(params, "fp32").decode(feat, ff, res, tt, (HH, WW), n_range=(0, n_take))
+    # flow_out is [2 * B * N, 2, HH, WW] with index r * N + n: compare the timestamps the fp32 path decoded
+    N = n_f16
+    for r in range(2):
+        assert (fa[r * N:r * N + n_take] - fb[r * N:r * N + n_take]).abs().max().item() < FLOW_TOL
+    d = (a[:n_take] - b[:n_take]).abs()
+    assert (d > TOL).float().mean().item() < 2e-3
+    assert torch.quantile(d.flatten()[::97].float(), 0.999).item() < TOL
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process (the reference's DataParallel case)")
+def test_two_devices_in_one_process():
+    """DataParallel drives several GPUs from one process (VideoSR_base_model.py:36): kernel attributes and the constant
+    bank are per device, so the second device must work after the first has initialised the library."""
+    from motif_b200 import synthetic
+    from motif_b200.correlation import FunctionCorrelation
+    from motif_b200.decoder import SpaceTimeDecoder
+    from motif_b200.softsplat_cp import FunctionSoftsplat
+
+    B, H, W, HH, WW = 1, 12, 16, 48, 64
+    lat = synthetic.synthetic_latents(B, H, W, seed=3)
+    params = synthetic.synthetic_params(seed=3)
+    tt = torch.tensor([[0.25, 0.75]])
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(dev):
+            dec = SpaceTimeDecoder(params, device=dev)
+            rgb, flow = dec.decode(*[t.to(dev) for t in lat], tt, (HH, WW))
+            x = torch.arange(2 * 130 * 40 * 64, dtype=torch.float32, device=dev).reshape(2, 130, 40, 64).sin()
+            fl = torch.full((2, 2, 40, 64), 1.25, device=dev)
+            o, n = FunctionSoftsplat(x, fl, -x[:, :1].abs(), "softmax")
+            c = FunctionCorrelation(x[:, :32].contiguous(), x[:, 32:64].contiguous())
+            outs.append([t.cpu() for t in (rgb, flow, o, n, c)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_state_dict_loader_accepts_full_checkpoint_layout():
     from motif_b200.decoder import SpaceTimeDecoder
 
