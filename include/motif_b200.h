@@ -96,6 +96,17 @@ int motif_flow_front(const float* fr0, const float* fr1, const float* flow, cons
                      void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * RAFT correlation lookup of one pyramid level.  Replaces alt_cuda_corr.forward as
+ * AlternateCorrBlock.__call__ uses it (models/core/corr.py:69-87; the module is a binary the reference does not ship);
+ * the in-repo definition of the quantity is CorrBlock (corr.py:8-56, utils/utils.py:57-70).
+ *   fmap1 [B, H, W, C]   fmap2 [B, H2, W2, C] (this level)   coords [B, H, W, 2] = (x, y) in pixels of this level
+ *   out [B, (2r+1)^2, H, W]: out[b, a*(2r+1)+c, y, x] = sum over the bilinear corners (zero outside fmap2) of
+ *        <fmap1[b,y,x,:], fmap2[b,yy,xx,:]> at (cx + a - r, cy + c - r)   -- NOT divided by sqrt(C) (corr.py:87 does that)
+ * ---------------------------------------------------------------------------------- */
+int motif_raft_corr_lookup(const float* fmap1, const float* fmap2, const float* coords, float* out, int B, int H, int W, int H2,
+                           int W2, int C, int r, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Space-time local implicit decoder.  Replaces models/modules/Ours.py:659-858 (LunaTokis.forward
  * from make_coord to the clamp) with SIREN MLPs of models/modules/SIREN.py:44-45, 76-79.
  * ---------------------------------------------------------------------------------- */

@@ -29,6 +29,7 @@ EXPORTS = [
     "motif_splat_count_fwd",
     "motif_corr_fwd",
     "motif_flow_front",
+    "motif_raft_corr_lookup",
     "motif_query_geometry",
     "motif_pack_latents",
     "motif_decode_workspace_bytes",
@@ -105,6 +106,8 @@ def _declare(lib):
     lib.motif_corr_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_flow_front.restype = c_int
     lib.motif_flow_front.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.motif_raft_corr_lookup.restype = c_int
+    lib.motif_raft_corr_lookup.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_query_geometry.restype = c_int
     lib.motif_query_geometry.argtypes = [POINTER(GeomT), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.motif_pack_latents.restype = c_int

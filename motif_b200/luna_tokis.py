@@ -29,6 +29,7 @@ import torch
 import torch.nn.functional as F
 from torch.nn.functional import interpolate
 
+from . import alt_cuda_corr
 from .decoder import SpaceTimeDecoder, hr_size_from_scale
 from .flow_front import flow_front
 from .softsplat_count_cp import Softsplat_Count
@@ -120,8 +121,12 @@ def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, tra
     return rgb, flow_out, 0.0  # Ours.py:580, 858: flow_GT = 0 on the inference path, returned as (0 / 20.0) / (HH / H)
 
 
-def install(model, precision: str = "f16x3"):
-    """Patch a reference ``LunaTokis`` instance in place and return it."""
+def install(model, precision: str = "f16x3", raft_lookup: bool = True):
+    """Patch a reference ``LunaTokis`` instance in place and return it.  ``raft_lookup``: answer the reference's
+    ``import alt_cuda_corr`` (``models/core/corr.py:5, 82`` -- a binary it does not ship) with ``motif_b200.alt_cuda_corr``,
+    so that the shipped ``alternate_corr=True`` RAFT (``Ours.py:417-430``) runs without materialising the all-pairs volume."""
+    if raft_lookup:
+        alt_cuda_corr.install()
     object.__setattr__(model, "_motif_precision", precision)
     model.fwarp = Softsplat()
     model.fwarp_max = Softsplat_Max()

@@ -162,6 +162,24 @@ def front_cases():
         _save(name, x=x, flow_hr=r["flow_hr"], g_filter=model.g_filter.detach().reshape(3, 3), flow_process_in=r["flow_process_in"])
 
 
+def raft_corr_case():
+    """RAFT correlation lookup: the reference's own CorrBlock class (models/core/corr.py:8-56) on seeded feature maps and
+    coordinates that leave the image on two sides (zero padding) and hit integer positions."""
+    ref_shims.import_reference()  # module stubs (alt_cuda_corr, cupy) + sys.path
+    from models.core.corr import CorrBlock  # the reference's class, imported from where it lies
+
+    g = torch.Generator().manual_seed(21)
+    B, C, H, W, r = 2, 32, 16, 24, 3  # coarsest level 2 x 3: bilinear_sampler divides by (H - 1)
+    fmap1, fmap2 = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    coords = torch.stack([xs, ys], 0)[None].repeat(B, 1, 1, 1) + torch.randn(B, 2, H, W, generator=g) * 3.0
+    coords[0, :, 0, 0] = torch.tensor([2.0, 3.0])      # exactly on a sample
+    coords[0, :, 0, 1] = torch.tensor([-5.0, 20.0])    # far outside
+    coords[1, :, 5, 5] = torch.tensor([W - 1.0, H - 1.0])
+    out = CorrBlock(fmap1, fmap2, num_levels=4, radius=r)(coords)
+    _save("raft_corr", fmap1=fmap1, fmap2=fmap2, coords=coords, radius=np.array([r]), out=out)
+
+
 def ensemble_case():
     # the reference's local_ensemble=True branch (four shifted latents, diagonally swapped area weights)
     decoder_case("decoder_ens_x3", (12, 16), 3, [0.4], 2, False, seed=3, gain=1.0, first_gain=4.0, alpha=-20.0, ensemble=True)
@@ -173,6 +191,9 @@ if __name__ == "__main__":
     if "--ensemble-only" in sys.argv:
         ensemble_case()
         raise SystemExit(0)
+    if "--raft-corr-only" in sys.argv:
+        raft_corr_case()
+        raise SystemExit(0)
     if "--front-only" in sys.argv:
         front_cases()
         raise SystemExit(0)
@@ -180,3 +201,4 @@ if __name__ == "__main__":
     correlation_cases()
     decoder_cases()
     front_cases()
+    raft_corr_case()

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from conftest import hot_params, load_golden
-from oracle import build_ref, correlation_ref, decoder_ref, flow_front_ref, softsplat_ref
+from oracle import build_ref, correlation_ref, decoder_ref, flow_front_ref, raft_corr_ref, softsplat_ref
 
 SPLAT_CASES = ["splat_s05", "splat_s4", "splat_s32"]
 
@@ -81,6 +81,17 @@ def test_flow_front_oracle_reproduces_reference_flow_process_input(case):
     out = flow_front_ref.flow_front(x[:, 0], x[:, 1], flow, g["g_filter"])
     assert out.shape == g["flow_process_in"].shape
     assert (out - g["flow_process_in"]).abs().max().item() < 1e-6
+
+
+def test_raft_corr_oracle_reproduces_reference_corr_block():
+    """models/core/corr.py:8-56: the reference's own CorrBlock class; and the per-level formulation that
+    AlternateCorrBlock / alt_cuda_corr must realise (corr.py:59-87) equals it."""
+    g = load_golden("raft_corr")
+    r = int(g["radius"][0])
+    a = raft_corr_ref.corr_block_lookup(g["fmap1"], g["fmap2"], g["coords"], 4, r)
+    assert (a - g["out"]).abs().max().item() < 1e-6
+    b = raft_corr_ref.alternate_corr_block_lookup(g["fmap1"], g["fmap2"], g["coords"], 4, r)
+    assert (b - g["out"]).abs().max().item() < 1e-5
 
 
 def test_hr_size_rounding_matches_reference_rule():
