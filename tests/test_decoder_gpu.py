@@ -293,8 +293,12 @@ def test_two_devices_in_one_process():
             o, n = FunctionSoftsplat(x, fl, -x[:, :1].abs(), "softmax")
             c = FunctionCorrelation(x[:, :32].contiguous(), x[:, 32:64].contiguous())
             outs.append([t.cpu() for t in (rgb, flow, o, n, c)])
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    names = ("rgb", "flow", "splat", "norm", "corr")
+    for name, a, b in zip(names, *outs):
+        if name == "rgb":  # the decoder's destination lists are filled in atomic order: fp32 sums differ in the last bits run to run
+            assert (a - b).abs().max().item() < 1e-5
+        else:
+            assert torch.equal(a, b), name
 
 
 def test_state_dict_loader_accepts_full_checkpoint_layout():
