@@ -133,3 +133,39 @@ def install(model, precision: str = "f16x3", raft_lookup: bool = True):
     model.fwarp_count = Softsplat_Count()
     model.forward = types.MethodType(forward_b200, model)
     return model
+
+
+def test_b200(self, output=False):
+    """Drop-in for ``VideoSRBaseModel.test`` (``models/VideoSR_base_model.py:169-197``) for the ``"Ours"`` networks.
+
+    The reference decodes the clip's timestamps in chunks of three and re-runs the WHOLE forward -- RAFT on four HR frame
+    pairs, the encoder, ``flow_process``, ``imnet`` -- for every chunk (``:188-193``), although none of that depends on the
+    timestamps.  Here the surround runs once and all timestamps are decoded by one call (the decoder groups them by eight
+    internally).  Attributes set as the reference sets them: ``fake_H [N,B,3,HH,WW]`` (the chunks were concatenated along
+    dim 0, ``:193``), ``flow`` = the flow of the LAST chunk (``:194``; index ``(r*B + b) * n_chunk + n``), ``flow_GT``."""
+    net = self.netG.module if hasattr(self.netG, "module") else self.netG
+    if not ("Ours" in self.net_base and self.net_base != "Ours_44") or self.times is None or not hasattr(net, "_motif_precision"):
+        return type(self)._motif_reference_test(self, output)
+    self.netG.eval()
+    with torch.no_grad():
+        fake_H, flow, flow_GT = self.netG(self.var_L, self.real_H, self.times, self.scale, use_GT=False, iter=4)
+        n_all = len(self.times)
+        last0 = 3 * ((n_all - 1) // 3)  # first timestamp of the reference's last chunk
+        two_b = flow.shape[0] // n_all
+        self.fake_H = fake_H
+        self.flow = flow.reshape(two_b, n_all, *flow.shape[1:])[:, last0:].reshape(two_b * (n_all - last0), *flow.shape[1:])
+        self.flow_GT = flow_GT
+    self.netG.train()
+    if output == True:  # noqa: E712  (as the reference writes it)
+        return self.fake_H
+
+
+def install_test(model_wrapper, precision: str = "f16x3"):
+    """``install`` on the wrapped ``LunaTokis`` plus the single-pass ``test`` above on a ``VideoSRBaseModel`` instance."""
+    net = model_wrapper.netG.module if hasattr(model_wrapper.netG, "module") else model_wrapper.netG
+    install(net, precision)
+    cls = type(model_wrapper)
+    if not hasattr(cls, "_motif_reference_test"):
+        cls._motif_reference_test = cls.test
+    model_wrapper.test = types.MethodType(test_b200, model_wrapper)
+    return model_wrapper

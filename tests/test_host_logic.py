@@ -115,3 +115,58 @@ def test_install_keeps_state_dict_layout_and_refuses_training():
     model.train()
     with pytest.raises(NotImplementedError):
         model(torch.rand(1, 2, 3, 32, 48), None, [torch.tensor([[0.5]])], 4, use_GT=False)
+
+
+def test_single_pass_test_equals_the_reference_chunk_loop():
+    """VideoSR_base_model.py:188-195: chunks of three timestamps concatenated along dim 0, `flow` of the last chunk --
+    reproduced by ONE forward over all timestamps (motif_b200.luna_tokis.test_b200)."""
+    from motif_b200 import luna_tokis
+
+    B, HH, WW = 2, 4, 6
+    calls = []
+
+    class FakeNet(torch.nn.Module):
+        _motif_precision = "f16x3"
+
+        def forward(self, x, real_h, times, scale, use_GT=True, iter=12):
+            calls.append(len(times))
+            n = len(times)
+            tt = torch.stack(times, 1).squeeze(-1)  # [B, n]
+            rgb = tt.t().reshape(n, B, 1, 1, 1).expand(n, B, 3, HH, WW).clone()
+            # flow index (r*B + b) * n + k, value encodes (r*B + b, t)
+            rb = torch.arange(2 * B).view(2 * B, 1).float()
+            flow = (rb * 10 + tt.repeat(2, 1)).reshape(2 * B * n, 1, 1, 1).expand(2 * B * n, 2, HH, WW).clone()
+            return rgb, flow, 0.0
+
+    class Wrapper:
+        net_base = "Ours"
+
+        def __init__(self, times):
+            self.netG, self.var_L, self.real_H, self.scale = FakeNet(), torch.zeros(B, 2, 3, 2, 3), None, 2
+            self.times = times
+
+        def test(self, output=False):  # the reference loop, VideoSR_base_model.py:169-197 ("Ours" branch)
+            self.netG.eval()
+            with torch.no_grad():
+                self.fake_H, flow, flow_GT = self.netG(self.var_L, self.real_H, self.times[:3], self.scale, use_GT=False, iter=4)
+                if len(self.times) != 3:
+                    for l in range(3, len(self.times), 3):
+                        tmp, flow, flow_GT = self.netG(self.var_L, None, self.times[l:l + 3], self.scale, use_GT=False, iter=4)
+                        self.fake_H = torch.cat((self.fake_H, tmp), 0)
+                self.flow, self.flow_GT = flow, flow_GT
+            self.netG.train()
+            if output:
+                return self.fake_H
+
+    for n_ts in (1, 3, 7, 11):
+        times = [torch.full((B, 1), (k + 1) / (n_ts + 1)) + torch.arange(B).view(B, 1) * 0.001 for k in range(n_ts)]
+        ref = Wrapper(times)
+        ref_out = ref.test(output=True)
+        calls.clear()
+        new = Wrapper(times)
+        new._motif_reference_test = None
+        type(new)._motif_reference_test = Wrapper.test
+        new.test = __import__("types").MethodType(luna_tokis.test_b200, new)
+        out = new.test(output=True)
+        assert calls == [n_ts]  # one forward for the whole clip
+        assert torch.equal(out, ref_out) and torch.equal(new.flow, ref.flow) and new.flow_GT == ref.flow_GT
