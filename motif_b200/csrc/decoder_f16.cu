@@ -243,6 +243,8 @@ struct LrJob {
 struct LrJobs {
   LrJob j[16];
 };
+// Two LR pixels per thread: every (broadcast) shared-memory load of a weight quad feeds eight FMAs instead of four -- the
+// kernel is bound by the LSU data pipe (a broadcast LDS.128 still writes 512 B back to the register file), not by FP32.
 __global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float* __restrict__ wp, int P) {
   __shared__ float4 w4[64 * 16];
   __shared__ float bias[64];
@@ -250,33 +252,43 @@ __global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) w4[i] = *reinterpret_cast<const float4*>(wp + jb.w_off + 4 * i);
   if (threadIdx.x < 64) bias[threadIdx.x] = jb.bias_off >= 0 ? wp[jb.bias_off + threadIdx.x * jb.bias_ld] : 0.0f;
   __syncthreads();
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  float x[64];
-  const float4* xr = reinterpret_cast<const float4*>(jb.x + (size_t)p * 64);
+  const int p0 = blockIdx.x * (2 * blockDim.x) + threadIdx.x, p1 = p0 + blockDim.x;
+  if (p0 >= P) return;
+  const bool two = p1 < P;
+  float x0[64], x1[64];
+  const float4* xr0 = reinterpret_cast<const float4*>(jb.x + (size_t)p0 * 64);
+  const float4* xr1 = reinterpret_cast<const float4*>(jb.x + (size_t)(two ? p1 : p0) * 64);
 #pragma unroll
   for (int k4 = 0; k4 < 16; ++k4) {
-    const float4 v = __ldg(xr + k4);
-    x[4 * k4] = v.x, x[4 * k4 + 1] = v.y, x[4 * k4 + 2] = v.z, x[4 * k4 + 3] = v.w;
+    const float4 v = __ldg(xr0 + k4), u = __ldg(xr1 + k4);
+    x0[4 * k4] = v.x, x0[4 * k4 + 1] = v.y, x0[4 * k4 + 2] = v.z, x0[4 * k4 + 3] = v.w;
+    x1[4 * k4] = u.x, x1[4 * k4 + 1] = u.y, x1[4 * k4 + 2] = u.z, x1[4 * k4 + 3] = u.w;
   }
-  float4* o4 = reinterpret_cast<float4*>(jb.out + (size_t)p * 64);
+  float4* o0 = reinterpret_cast<float4*>(jb.out + (size_t)p0 * 64);
+  float4* o1 = reinterpret_cast<float4*>(jb.out + (size_t)(two ? p1 : p0) * 64);
 #pragma unroll 1
-  for (int o0 = 0; o0 < 64; o0 += 4) {
-    float r[4];
+  for (int og = 0; og < 64; og += 4) {
+    float r0[4], r1[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      float a0 = 0.f, a1 = 0.f;
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
       for (int k4 = 0; k4 < 16; ++k4) {
-        const float4 w = w4[(o0 + u) * 16 + k4];
-        a0 = fmaf(w.x, x[4 * k4], a0);
-        a1 = fmaf(w.y, x[4 * k4 + 1], a1);
-        a0 = fmaf(w.z, x[4 * k4 + 2], a0);
-        a1 = fmaf(w.w, x[4 * k4 + 3], a1);
+        const float4 w = w4[(og + u) * 16 + k4];
+        a0 = fmaf(w.x, x0[4 * k4], a0);
+        a1 = fmaf(w.y, x0[4 * k4 + 1], a1);
+        a0 = fmaf(w.z, x0[4 * k4 + 2], a0);
+        a1 = fmaf(w.w, x0[4 * k4 + 3], a1);
+        b0 = fmaf(w.x, x1[4 * k4], b0);
+        b1 = fmaf(w.y, x1[4 * k4 + 1], b1);
+        b0 = fmaf(w.z, x1[4 * k4 + 2], b0);
+        b1 = fmaf(w.w, x1[4 * k4 + 3], b1);
       }
-      r[u] = ((a0 + a1) + bias[o0 + u]) * kOmega;
+      r0[u] = ((a0 + a1) + bias[og + u]) * kOmega;
+      r1[u] = ((b0 + b1) + bias[og + u]) * kOmega;
     }
-    o4[o0 >> 2] = make_float4(r[0], r[1], r[2], r[3]);
+    o0[og >> 2] = make_float4(r0[0], r0[1], r0[2], r0[3]);
+    if (two) o1[og >> 2] = make_float4(r1[0], r1[1], r1[2], r1[3]);
   }
 }
 
@@ -1549,7 +1561,7 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
     lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.p0i + (size_t)rb * P * 64, Wp::i_a0, -1, 0};
     lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.ftab + (size_t)rb * P * 64, Wp::s_a0b, -1, 0};
     if (nj + 4 > 16) {
-      lr_tables_kernel<<<dim3(ceil_div(P, 128), nj), 128, 0, st>>>(lj, sc.wpack, P);
+      lr_tables_kernel<<<dim3(ceil_div(P, 256), nj), 128, 0, st>>>(lj, sc.wpack, P);
       MOTIF_LAUNCHED("lr_tables_kernel");
       nj = 0;
     }
@@ -1557,13 +1569,13 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
   for (int b = 0; b < B; ++b) {
     lj.j[nj++] = LrJob{a->residual + (size_t)b * P * 64, sc.rtab + (size_t)b * P * 64, Wp::s_a0c, Wp::s_e0, 8};
     if (nj == 16) {
-      lr_tables_kernel<<<dim3(ceil_div(P, 128), nj), 128, 0, st>>>(lj, sc.wpack, P);
+      lr_tables_kernel<<<dim3(ceil_div(P, 256), nj), 128, 0, st>>>(lj, sc.wpack, P);
       MOTIF_LAUNCHED("lr_tables_kernel");
       nj = 0;
     }
   }
   if (nj > 0) {
-    lr_tables_kernel<<<dim3(ceil_div(P, 128), nj), 128, 0, st>>>(lj, sc.wpack, P);
+    lr_tables_kernel<<<dim3(ceil_div(P, 256), nj), 128, 0, st>>>(lj, sc.wpack, P);
     MOTIF_LAUNCHED("lr_tables_kernel");
   }
   return 0;
