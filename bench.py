@@ -295,7 +295,7 @@ def main():
         tensor_peak, peak_name = peaks["bf16_sustained"], "fp16 dense = bf16 sustained"
     else:
         tensor_peak, peak_name = peaks["bf16_sustained"] / 2.0, "TF32 dense = 0.5 x bf16 sustained"
-    traffic = load_traffic()
+    traffic = load_traffic() if world == 1 else {}  # the committed ncu capture is of the single-GPU launch (all 7 timestamps per launch)
     kernels = {}
     per_clip = ("imnet_kernel", "imnet_tc_kernel", "imnet_f16_kernel")
     for k, (tot_ms, cnt) in live.items():
