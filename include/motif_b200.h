@@ -107,6 +107,16 @@ int motif_raft_corr_lookup(const float* fmap1, const float* fmap2, const float* 
                            int W2, int C, int r, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Modulated deformable convolution (DCNv2) forward, 3x3 / stride 1 / padding 1 / dilation 1.  Replaces
+ * dcn_v2_forward of the reference's extension (models/modules/DCNv2/dcn_v2.py:13-47, src/cuda/dcn_v2_im2col_cuda.cu:25-55,
+ * 125-195 + the SGEMM of src/cuda/dcn_v2_cuda.cu), which cannot be built on torch 2.x (THC).
+ *   in [B, Cin, H, W]   offset [B, dg*18, H, W] (per group and tap: dh, dw)   mask [B, dg*9, H, W]
+ *   weight [Cout, Cin, 3, 3]   bias [Cout] or NULL   out [B, Cout, H, W];   Cin / dg <= 8
+ * ---------------------------------------------------------------------------------- */
+int motif_dcn_v2_fwd(const float* in, const float* offset, const float* mask, const float* weight, const float* bias, float* out,
+                     int B, int Cin, int Cout, int H, int W, int deformable_groups, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Space-time local implicit decoder.  Replaces models/modules/Ours.py:659-858 (LunaTokis.forward
  * from make_coord to the clamp) with SIREN MLPs of models/modules/SIREN.py:44-45, 76-79.
  * ---------------------------------------------------------------------------------- */

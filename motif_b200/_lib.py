@@ -30,6 +30,7 @@ EXPORTS = [
     "motif_corr_fwd",
     "motif_flow_front",
     "motif_raft_corr_lookup",
+    "motif_dcn_v2_fwd",
     "motif_query_geometry",
     "motif_pack_latents",
     "motif_decode_workspace_bytes",
@@ -108,6 +109,8 @@ def _declare(lib):
     lib.motif_flow_front.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_raft_corr_lookup.restype = c_int
     lib.motif_raft_corr_lookup.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.motif_dcn_v2_fwd.restype = c_int
+    lib.motif_dcn_v2_fwd.argtypes = [c_void_p] * 6 + [c_int] * 6 + [c_void_p]
     lib.motif_query_geometry.restype = c_int
     lib.motif_query_geometry.argtypes = [POINTER(GeomT), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.motif_pack_latents.restype = c_int

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from conftest import hot_params, load_golden
-from oracle import build_ref, correlation_ref, decoder_ref, flow_front_ref, raft_corr_ref, softsplat_ref
+from oracle import build_ref, correlation_ref, dcn_v2_ref, decoder_ref, flow_front_ref, raft_corr_ref, softsplat_ref
 
 SPLAT_CASES = ["splat_s05", "splat_s4", "splat_s32"]
 
@@ -92,6 +92,23 @@ def test_raft_corr_oracle_reproduces_reference_corr_block():
     assert (a - g["out"]).abs().max().item() < 1e-6
     b = raft_corr_ref.alternate_corr_block_lookup(g["fmap1"], g["fmap2"], g["coords"], 4, r)
     assert (b - g["out"]).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("sigma", [0.0, 2.5, 40.0])
+def test_dcn_v2_oracle_against_torchvision(sigma):
+    """models/modules/DCNv2 cannot be built on torch 2.x (THC) and has no test: the restatement of its im2col + product
+    (dcn_v2_im2col_cuda.cu:25-55, 125-195) is pinned against torchvision's deform_conv2d, a third-party implementation of
+    the same algorithm (the stand-in the decoder goldens were generated with)."""
+    tv = pytest.importorskip("torchvision")
+    g = torch.Generator().manual_seed(int(sigma) + 1)
+    B, Cin, Cout, H, W, dg = 2, 16, 12, 9, 11, 4
+    x = torch.randn(B, Cin, H, W, generator=g)
+    off = torch.randn(B, dg * 18, H, W, generator=g) * sigma
+    m = torch.rand(B, dg * 9, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * 0.1
+    b = torch.randn(Cout, generator=g)
+    a = dcn_v2_ref.dcn_v2_conv(x, off, m, w, b, 1, 1, 1, dg)
+    assert (a - tv.ops.deform_conv2d(x, off, w, b, 1, 1, 1, m)).abs().max().item() < 1e-5
 
 
 def test_hr_size_rounding_matches_reference_rule():

@@ -13,6 +13,7 @@ timeout 300 python tools/bench_splat.py 2>&1 | tail -8 | tee gpurun_out/${tag}_s
 timeout 300 python tools/bench_ref_gpu.py 2>&1 | tail -12 | tee gpurun_out/${tag}_ref_gpu.txt
 timeout 300 python tools/bench_front.py 2>&1 | tail -4 | tee gpurun_out/${tag}_front.txt
 timeout 300 python tools/bench_raft_corr.py 2>&1 | tail -3 | tee gpurun_out/${tag}_raft_corr.txt
+timeout 300 python tools/bench_dcn.py 2>&1 | tail -2 | tee gpurun_out/${tag}_dcn.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/${tag}_launches.log 2>&1; echo "ncu list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gather_l0_kernel|flow_bin_q_kernel|synth_q_kernel|imnet_f16_kernel|splat_gather' -s 4 -c 6 \
