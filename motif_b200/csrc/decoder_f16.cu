@@ -1323,7 +1323,11 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
   const int bn = b * N + n0 + nl;
   uint32_t* a0_out = sc.a0 + (((size_t)nl * B + b) * ((size_t)blocks_x * blocks_y) * (kGW * kGH) + ((size_t)blk * kGH + warp) * kGW) * 64;
 
-#pragma unroll 1
+#ifndef MOTIF_GATHER_UNROLL
+#define MOTIF_GATHER_UNROLL 1
+#endif
+  constexpr int kGatherUnroll = MOTIF_GATHER_UNROLL;
+#pragma unroll kGatherUnroll
   for (int it = 0; it < kGW / 2; ++it) {
     const int j = 2 * it + h;  // this half-warp's destination
     const float4 pa = par_s[warp][j][0], pb = par_s[warp][j][1];
