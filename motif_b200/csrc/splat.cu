@@ -39,11 +39,12 @@ static size_t workspace_layout(int n, int h, int w, SplatWorkspace* ws, char* ba
     off += align256(bytes);
     return ptr;
   };
+  // count | ovf_mask | ovf_total first and back to back: one memset arms a call
   char* a = take(p * sizeof(int));
-  char* b = take(p * sizeof(int) * kBinSlots);
-  char* c = take(p * sizeof(float) * kBinSlots);
   char* d = take(p);
   char* e = take(256);
+  char* b = take(p * sizeof(int) * kBinSlots);
+  char* c = take(p * sizeof(float) * kBinSlots);
   char* f = take(p * sizeof(int));
   if (ws) {
     ws->ovf_list = (int*)f;
@@ -71,15 +72,10 @@ __device__ __forceinline__ float metric_scale(const float* metric, size_t idx) {
 // only_overflow: contribute only the corners flagged in ovf_mask (surplus of the binning pass).
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restrict__ in, const float* __restrict__ flow,
-                                                            const float* __restrict__ metric, float* __restrict__ out,
-                                                            int n, int c, int h, int w,
-                                                            const unsigned char* __restrict__ ovf_mask,
-                                                            const int* __restrict__ ovf_total) {
+__device__ __forceinline__ void splat_scatter_dense(const float* __restrict__ in, const float* __restrict__ flow,
+                                                    const float* __restrict__ metric, float* __restrict__ out,
+                                                    int n, int c, int h, int w, const unsigned char* __restrict__ ovf_mask) {
   const int hw = h * w;
-  // surplus pass: this (thread per source, neighbouring sources coalesce) kernel takes the dense regime, the
-  // warp-per-listed-source kernel the sparse one; both are launched and one of them returns at once
-  if (ovf_total != nullptr && !surplus_is_dense(*ovf_total, (long long)n * hw)) return;
   const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < (long long)n * hw;
        p += (long long)gridDim.x * blockDim.x) {
@@ -120,6 +116,14 @@ __global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restr
   }
 }
 
+// the reference algorithm as an operator of its own (motif_splat_fwd_atomic)
+template <int MODE>
+__global__ void __launch_bounds__(256) splat_scatter_kernel(const float* __restrict__ in, const float* __restrict__ flow,
+                                                            const float* __restrict__ metric, float* __restrict__ out,
+                                                            int n, int c, int h, int w) {
+  splat_scatter_dense<MODE>(in, flow, metric, out, n, c, h, w, nullptr);
+}
+
 // Surplus of the binning pass: one WARP per listed source pixel, lanes over channels (the list is sparse, so a thread
 // per source would leave most of a warp idle and serialise 130 channels of atomics behind one thread).
 template <int MODE>
@@ -129,7 +133,11 @@ __global__ void __launch_bounds__(256) splat_scatter_list_kernel(const float* __
   const int hw = h * w;
   const int c_out = (MODE == MOTIF_SPLAT_SUMMATION) ? c : c + 1;
   const int n_list = *ws.ovf_total;
-  if (surplus_is_dense(n_list, (long long)n * hw)) return;
+  if (n_list == 0) return;
+  if (surplus_is_dense(n_list, (long long)n * hw)) {  // many overflowed sources: thread per source (neighbours coalesce), same launch
+    splat_scatter_dense<MODE>(in, flow, metric, out, n, c, h, w, ws.ovf_mask);
+    return;
+  }
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_list; i += warps) {
@@ -553,23 +561,20 @@ static int grid_for(long long work, int block) {
 }
 
 template <int MODE>
-static int launch_scatter(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w,
-                          const unsigned char* mask, const int* total, cudaStream_t st) {
-  {
-    ProfScope prof("splat_scatter_kernel", st);
-    splat_scatter_kernel<MODE><<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, metric, out, n, c, h, w, mask, total);
-    MOTIF_LAUNCHED("splat_scatter_kernel");
-  }
+static int launch_scatter(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w, cudaStream_t st) {
+  ProfScope prof("splat_scatter_kernel", st);
+  splat_scatter_kernel<MODE><<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, metric, out, n, c, h, w);
+  MOTIF_LAUNCHED("splat_scatter_kernel");
   return 0;
 }
 
+// Surplus of the binning pass (destinations with more than kBinSlots contributions): ONE launch, which returns at once
+// when nothing overflowed, takes a warp per listed source when few did and a thread per source when many did.
 template <int MODE>
 static int launch_surplus(const float* in, const float* flow, const float* metric, float* out, int n, int c, int h, int w, const SplatWorkspace& ws,
                           cudaStream_t st) {
   ProfScope prof("splat_scatter_kernel", st);
-  splat_scatter_list_kernel<MODE><<<148 * 4, 256, 0, st>>>(in, flow, metric, out, n, c, h, w, ws);
-  MOTIF_LAUNCHED("splat_scatter_kernel");
-  splat_scatter_kernel<MODE><<<grid_for((long long)n * h * w, 256), 256, 0, st>>>(in, flow, metric, out, n, c, h, w, ws.ovf_mask, ws.ovf_total);
+  splat_scatter_list_kernel<MODE><<<148 * 8, 256, 0, st>>>(in, flow, metric, out, n, c, h, w, ws);
   MOTIF_LAUNCHED("splat_scatter_kernel");
   return 0;
 }
@@ -624,10 +629,10 @@ extern "C" int motif_splat_fwd_atomic(const float* in, const float* flow, const 
   const int c_out = mode == MOTIF_SPLAT_SUMMATION ? c : c + 1;
   MOTIF_CUDA(cudaMemsetAsync(out, 0, (size_t)n * c_out * h * w * sizeof(float), st));
   switch (mode) {
-    case MOTIF_SPLAT_SUMMATION: return launch_scatter<MOTIF_SPLAT_SUMMATION>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
-    case MOTIF_SPLAT_AVERAGE: return launch_scatter<MOTIF_SPLAT_AVERAGE>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
-    case MOTIF_SPLAT_LINEAR: return launch_scatter<MOTIF_SPLAT_LINEAR>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
-    default: return launch_scatter<MOTIF_SPLAT_SOFTMAX>(in, flow, metric, out, n, c, h, w, nullptr, nullptr, st);
+    case MOTIF_SPLAT_SUMMATION: return launch_scatter<MOTIF_SPLAT_SUMMATION>(in, flow, metric, out, n, c, h, w, st);
+    case MOTIF_SPLAT_AVERAGE: return launch_scatter<MOTIF_SPLAT_AVERAGE>(in, flow, metric, out, n, c, h, w, st);
+    case MOTIF_SPLAT_LINEAR: return launch_scatter<MOTIF_SPLAT_LINEAR>(in, flow, metric, out, n, c, h, w, st);
+    default: return launch_scatter<MOTIF_SPLAT_SOFTMAX>(in, flow, metric, out, n, c, h, w, st);
   }
 }
 
@@ -641,9 +646,7 @@ extern "C" int motif_splat_fwd(const float* in, const float* flow, const float* 
   SplatWorkspace ws;
   workspace_layout(n, h, w, &ws, (char*)workspace);
   const size_t p = (size_t)n * h * w;
-  MOTIF_CUDA(cudaMemsetAsync(ws.count, 0, p * sizeof(int), st));
-  MOTIF_CUDA(cudaMemsetAsync(ws.ovf_mask, 0, p, st));
-  MOTIF_CUDA(cudaMemsetAsync(ws.ovf_total, 0, sizeof(int), st));
+  MOTIF_CUDA(cudaMemsetAsync(ws.count, 0, (size_t)((char*)ws.ovf_total - (char*)ws.count) + sizeof(int), st));  // count, ovf_mask, ovf_total
   {
     ProfScope prof("splat_bin_kernel", st);
     splat_bin_kernel<<<grid_for((long long)p, 256), 256, 0, st>>>(flow, ws, n, h, w);
