@@ -23,7 +23,7 @@ from .decoder import SpaceTimeDecoder
 
 
 class ClipStream:
-    def __init__(self, decoder: SpaceTimeDecoder, depth: int = 2, distributed: bool = False, src: int = 0, group=None):
+    def __init__(self, decoder: SpaceTimeDecoder, depth: int = 2, distributed: bool = False, src: int = 0, group=None, return_flow: bool = False):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.dec = decoder
@@ -32,6 +32,7 @@ class ClipStream:
         self.distributed = distributed
         self.src = src
         self.group = group
+        self.return_flow = return_flow  # also produce the forward's second output (flow / 20 / (HH/H), Ours.py:858) on the device
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
         self._slots = [None] * depth
@@ -41,6 +42,12 @@ class ClipStream:
         i = k % self.depth
         sl = self._slots[i]
         if sl is None or sl["shapes"] != shapes or sl["out"].shape != out_shape:
+            if sl is not None:
+                # the old buffers may still be the target / source of copies in flight on the side streams: tell the
+                # caching allocator (they were allocated on the compute stream) before dropping them
+                for t in sl["lat"]:
+                    t.record_stream(self.s_in)
+                sl["out"].record_stream(self.s_out)
             sl = {"shapes": shapes,
                   "lat": [torch.empty(s, dtype=torch.float32, device=self.dev) for s in shapes],
                   "out": torch.empty(out_shape, dtype=torch.float32, device=self.dev),
@@ -83,7 +90,7 @@ class ClipStream:
         lat = sl["lat"]
         if self.distributed:
             lat = sharding.broadcast_latents(*lat, src=self.src, group=self.group)
-        self.dec.decode(lat[0], lat[1], lat[2], tt, (HH, WW), n_range=(n0, n1), return_flow=False, out=sl["out"])
+        self.dec.decode(lat[0], lat[1], lat[2], tt, (HH, WW), n_range=(n0, n1), return_flow=self.return_flow, out=sl["out"])
         sl["ev_done"].record(compute)
         sl["ev_free"] = sl["ev_done"]
         if out_h is not None and n1 > n0:

@@ -24,6 +24,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "decoder_common.cuh"
 #include "tc_common.cuh"
 
@@ -142,10 +144,9 @@ static int layout(int B, int NT, int H, int W, int HH, int WW, Scratch* s, char*
   t.wimg = (unsigned char*)take((size_t)kNumImg * kBlkBytes);
   t.out3c = (float*)take(sizeof(float) * 2 * 1024);
   t.qctr = (int*)take(sizeof(int) * 8);
-  t.p0f = (float*)take(sizeof(float) * 2 * B * P * 64);
-  t.p0i = (float*)take(sizeof(float) * 2 * B * P * 64);
-  t.ftab = (float*)take(sizeof(float) * 2 * B * P * 64);
-  t.rtab = (float*)take(sizeof(float) * B * P * 64);
+  // Everything whose offset the arming invariant depends on comes BEFORE the LR tables: the armed region then sits at
+  // offsets that depend on (B, NT, HH, WW) only, and the magic words carry (H, W) as well, so a decoder reused for the
+  // same HR size at another LR size (arbitrary-scale evaluation) never mistakes stale data for armed accumulators.
   t.Y = (float*)take(sizeof(float) * 2 * B * qs * 64);
   const size_t z0 = off;
   t.side = (float*)take(sizeof(float) * NT * B * qs * 4);
@@ -155,6 +156,10 @@ static int layout(int B, int NT, int H, int W, int HH, int WW, Scratch* s, char*
   t.zmax = (float*)take(sizeof(float) * NT * B * qs);
   t.bin_ent = (uint2*)take(sizeof(uint2) * NT * B * qs * kSlots);
   t.a0 = (uint32_t*)take(sizeof(uint32_t) * 64 * NT * B * (size_t)((WW + kGWh - 1) / kGWh) * ((HH + kGHh - 1) / kGHh) * (kGWh * kGHh));
+  t.p0f = (float*)take(sizeof(float) * 2 * B * P * 64);
+  t.p0i = (float*)take(sizeof(float) * 2 * B * P * 64);
+  t.ftab = (float*)take(sizeof(float) * 2 * B * P * 64);
+  t.rtab = (float*)take(sizeof(float) * B * P * 64);
   if (s) *s = t;
   if (bytes) *bytes = off;
   return 0;
@@ -1501,6 +1506,13 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+// Per-device host state of the f16x3 path (function attributes, owner of the constant bank), shared by every host thread
+// that decodes (the reference wraps the model in DataParallel: one worker thread per GPU, VideoSR_base_model.py:36).
+static std::mutex g_decode_mutex;
+static const void* g_bank_owner[64] = {nullptr};
+static cudaEvent_t g_bank_event[64];
+static bool g_bank_event_ok[64] = {false};
+
 // Weight-dependent images (clip-invariant): skipped when the caller vouches that the workspace still holds them.
 static int prepare_weights(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) {
   using Wp = WeightPack;
@@ -1546,14 +1558,15 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
     if (int rc = prepare_weights(a, sc, st)) return rc;
 #ifndef MOTIF_OUT3_SMEM
   {
-    // The constant bank is per device, not per workspace: re-upload when another workspace's constants are in it.
-    // (Two decoders with DIFFERENT weights decoding concurrently on two streams of one device would race on it.)
-    static const void* owner[64] = {nullptr};
-    int dev = 0;
-    MOTIF_CUDA(cudaGetDevice(&dev));
-    if (!a->weights_ready || owner[dev & 63] != (const void*)sc.out3c) {
+    // The constant bank is per device, not per workspace: re-upload when another workspace's constants are in it.  The
+    // caller (decode_f16) holds g_decode_mutex for its whole launch sequence, and the upload is ordered behind the last
+    // decode that READ the bank (any stream of this device) through bank_event: two decoders with different weights on
+    // two streams or host threads of one GPU serialise at this point instead of corrupting each other's kernels.
+    const int dev = current_device_slot();
+    if (!a->weights_ready || g_bank_owner[dev] != (const void*)sc.out3c) {
+      if (g_bank_event_ok[dev]) MOTIF_CUDA(cudaStreamWaitEvent(st, g_bank_event[dev], 0));
       MOTIF_CUDA(cudaMemcpyToSymbolAsync(c_out3, sc.out3c, sizeof(c_out3), 0, cudaMemcpyDeviceToDevice, st));
-      owner[dev & 63] = (const void*)sc.out3c;
+      g_bank_owner[dev] = (const void*)sc.out3c;
     }
   }
 #endif
@@ -1620,6 +1633,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   layout(g.B, NT, g.H, g.W, g.HH, g.WW, &sc, (char*)a->workspace, &need);
   if (a->workspace_bytes < need) return fail(MOTIF_E_WORKSPACE, "decode: workspace %zu < %zu bytes", a->workspace_bytes, need);
   if (a->n_begin == a->n_end) return 0;
+  std::lock_guard<std::mutex> lock(g_decode_mutex);  // launches only (asynchronous): ~0.1 ms of host time per clip
   MOTIF_REQUIRE(a->dbg_synth_in == nullptr, "decode: dbg_synth_in is only produced by precision fp32 / tf32x3 (f16x3 never forms the 198-channel input)");
   const size_t qs = (size_t)g.HH * g.WW;
   const int smem_fq = (int)sizeof(QSmemF) + 1024, smem_sq = (int)sizeof(QSmemS) + 1024, smem_i = (int)sizeof(SmemI) + 1024;
@@ -1646,7 +1660,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   // arm the destination accumulators (a no-op when the previous decode on this workspace completed, see arm_kernel)
   Magic magic, none;
   magic.w[0] = 0x4d6f5449u, magic.w[1] = ((uint32_t)g.B << 16) ^ (uint32_t)NT ^ 0x9e3779b9u;
-  magic.w[2] = (uint32_t)g.HH, magic.w[3] = (uint32_t)g.WW;
+  magic.w[2] = ((uint32_t)g.HH << 16) ^ (uint32_t)g.H ^ 0x85ebca6bu, magic.w[3] = ((uint32_t)g.WW << 16) ^ (uint32_t)g.W ^ 0xc2b2ae35u;
   none.w[0] = none.w[1] = none.w[2] = none.w[3] = 0u;
   arm_kernel<<<n_sm * 8, 256, 0, st>>>(sc.armed, magic, reinterpret_cast<uint4*>(sc.side), sc.zero_bytes / 16, sc.zmax, (size_t)NT * g.B * qs);
   MOTIF_LAUNCHED("arm_kernel");
@@ -1692,6 +1706,16 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   }
   mark_kernel<<<1, 32, 0, st>>>(sc.armed, magic);
   MOTIF_LAUNCHED("mark_kernel");
+#ifndef MOTIF_OUT3_SMEM
+  {
+    const int dev = current_device_slot();
+    if (!g_bank_event_ok[dev]) {
+      MOTIF_CUDA(cudaEventCreateWithFlags(&g_bank_event[dev], cudaEventDisableTiming));
+      g_bank_event_ok[dev] = true;
+    }
+    MOTIF_CUDA(cudaEventRecord(g_bank_event[dev], st));  // the last reader of the constant bank so far
+  }
+#endif
   return 0;
 }
 

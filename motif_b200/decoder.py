@@ -217,7 +217,9 @@ class SpaceTimeDecoder:
             a.precision = PRECISIONS[precision or self.precision]
             a.local_ensemble = int(self.local_ensemble)
             # the weight images in the workspace are clip-invariant: repacked only when the workspace or the arithmetic changed
-            ws_key = (ws.data_ptr(), a.precision)
+            # (the parameters may alias live model tensors -- .to() is a no-op for cuda fp32 -- so their version counters are
+            # part of the key: an in-place update by the owner of the weights forces a repack)
+            ws_key = (ws.data_ptr(), a.precision, self.alpha, tuple(t._version for t in self.params.values()))
             a.weights_ready = int(self._ws_weights_key == ws_key)
             self._ws_weights_key = None  # a failing call leaves the workspace in an unknown state
             rc = lib.motif_decode(ctypes.byref(a), _lib.current_stream_ptr(dev))

@@ -26,7 +26,6 @@ from __future__ import annotations
 import types
 
 import torch
-import torch.nn.functional as F
 from torch.nn.functional import interpolate
 
 from . import alt_cuda_corr
@@ -37,9 +36,15 @@ from .softsplat_cp import Softsplat
 from .softsplat_max_cp import Softsplat_Max
 
 
-def surround(self, x, target_t, scale, iter=12):
+def surround(self, x, target_t, scale, iter=12, front=flow_front):
     """``Ours.py:512-638``: everything before the hot path.  Returns
-    ``(feat [2B,64,H,W], flow_feat [2B,64,H,W], residual [B,64,H,W], target_t [B,N], (HH, WW))``."""
+    ``(feat [2B,64,H,W], flow_feat [2B,64,H,W], residual [B,64,H,W], target_t [B,N], (HH, WW))``.
+
+    ``front``: the operator that turns the LR frames and flows into the ``flow_process`` input (``Ours.py:562-578,
+    613-637``); the product's is the fused CUDA kernel ``motif_b200.flow_front`` (CUDA tensors only -- there is no eager
+    branch here; the CPU glue test passes the oracle's restatement, ``oracle/flow_front_ref.py``)."""
+    if self.trans or not self.input_Z:
+        raise NotImplementedError("motif_b200 runs the shipped front end (trans=False, input_Z=True; Ours.py:613-637)")
     x = x.permute(0, 2, 1, 3, 4)
     x = x[:, :, x.shape[2] // 2 - 1:x.shape[2] // 2 + 1]
     with torch.no_grad():
@@ -58,46 +63,12 @@ def surround(self, x, target_t, scale, iter=12):
         flow[0] *= 0.0
         flow[3] *= 0.0
         flow = flow.reshape(4 * B, 2, H, W)
-
-        fused_front = flow.is_cuda and not (self.trans or not self.input_Z)
-        if fused_front:  # Ours.py:562-578 + 613-637 in one kernel (motif_flow_front)
-            front_in = flow_front(fr0.float(), fr1.float(), flow.float(), self.g_filter)
-    if fused_front:
-        feat = self.encoder(torch.stack([fr0, fr1], 1), None)
-        residual = feat[:, feat.shape[1] // 2].reshape(B, -1, H, W)
-        feat = torch.cat((feat[:, feat.shape[1] // 2 - 1], feat[:, feat.shape[1] // 2 + 1]), 0)
-        return feat, self.flow_process(front_in), residual, target_t, (HH, WW)
-    with torch.no_grad():
-        # reliability maps psi_photo, psi_flow, psi_var (Ours.py:562-578)
-        warped, _ = self.bwarp(torch.cat([fr0, fr1, fr0, fr1], dim=0), flow)
-        psi_photo = F.l1_loss(input=torch.cat([fr0, fr0, fr1, fr1], dim=0), target=warped, reduction="none").mean(1)
-        flow = flow.reshape(4, B, 2, H, W)
-        warped, _ = self.bwarp(-torch.cat([flow[0], flow[2], flow[1], flow[3]], dim=0), flow.reshape(4 * B, 2, H, W))
-        psi_flow = F.l1_loss(input=flow.reshape(4 * B, 2, H, W), target=warped, reduction="none").mean(1)
-        f = flow.reshape(4 * B, -1, H, W)
-        sq_mean, mean_sq = torch.split(
-            F.conv3d(F.pad(torch.cat([f ** 2, f], 1), (1, 1, 1, 1), mode="reflect").unsqueeze(1), self.g_filter).squeeze(1), 2, dim=1)
-        psi_var = (sq_mean - mean_sq ** 2).clip(1e-9, None).sqrt().mean(1)
-        psies = torch.stack([psi_photo, psi_flow / 10.0, psi_var], dim=1)
-
+        front_in = front(fr0.float(), fr1.float(), flow.float(), self.g_filter)  # Ours.py:562-578 + 613-637
     # encoder features (Ours.py:601-611)
     feat = self.encoder(torch.stack([fr0, fr1], 1), None)
     residual = feat[:, feat.shape[1] // 2].reshape(B, -1, H, W)
     feat = torch.cat((feat[:, feat.shape[1] // 2 - 1], feat[:, feat.shape[1] // 2 + 1]), 0)
-
-    # flow encoder input: [flow / 20, psies, ref_start_durations / 8] (Ours.py:613-638, trans=False, input_Z=True)
-    flow = flow.reshape(4 * B, 2, H, W)
-    durations = torch.tensor([[0, 0], [0, 8], [8, 0], [8, 8]], dtype=torch.float32, device=flow.device).unsqueeze(1)
-    flow_feat = torch.cat(
-        (
-            (flow / 20.0).reshape(2, 2, B, -1, H, W).permute(0, 2, 1, 3, 4, 5).reshape(2 * B, 2, -1, H, W),
-            psies.reshape(2, 2, B, -1, H, W).permute(0, 2, 1, 3, 4, 5).reshape(2 * B, 2, -1, H, W),
-            durations.reshape(2, 4, 1, 1).unsqueeze(1).repeat(1, B, 1, H, W).reshape(2 * B, 2, 2, H, W) / 8.0,
-        ),
-        dim=2,
-    ).reshape(2 * B, -1, H, W)
-    flow_feat = self.flow_process(flow_feat)
-    return feat, flow_feat, residual, target_t, (HH, WW)
+    return feat, self.flow_process(front_in), residual, target_t, (HH, WW)
 
 
 def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, train_idx=0, use_GT=True, iter=12, flows=None):
@@ -109,14 +80,18 @@ def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, tra
             raise NotImplementedError(f"motif_b200 decodes the shipped configuration (setting 5); {flag}={getattr(self, flag)} is not supported")
     with torch.no_grad():
         feat, flow_feat, residual, tt, (HH, WW) = surround(self, x, target_t, scale, iter)
-        dec = getattr(self, "_motif_decoder", None)
+        # One decoder (weights + workspace) per device.  DataParallel replicas are shallow copies of the module, so they
+        # share this dict and each finds (or builds, from ITS OWN parameters) the decoder of the device it runs on.
+        cache = self.__dict__.setdefault("_motif_decoders", {})
         sd_version = sum(p._version for p in self.parameters())
         ens = bool(getattr(self, "local_ensemble", False))  # Ours.py:453; the four-latent ensemble runs on the fp32 path
-        if dec is None or dec.device != feat.device or self._motif_decoder_version != sd_version or dec.local_ensemble != ens:
+        key = (feat.device.type, feat.device.index)
+        hit = cache.get(key)
+        if hit is None or hit[1] != sd_version or hit[0].local_ensemble != ens:
             dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, local_ensemble=ens,
                                                    precision="fp32" if ens else getattr(self, "_motif_precision", "f16x3"))
-            object.__setattr__(self, "_motif_decoder", dec)
-            object.__setattr__(self, "_motif_decoder_version", sd_version)
+            cache[key] = (dec, sd_version)
+        dec = cache[key][0]
         rgb, flow_out = dec.decode(feat.float(), flow_feat.float(), residual.float(), tt, (HH, WW))
     return rgb, flow_out, 0.0  # Ours.py:580, 858: flow_GT = 0 on the inference path, returned as (0 / 20.0) / (HH / H)
 
@@ -131,7 +106,11 @@ def install(model, precision: str = "f16x3", raft_lookup: bool = True):
     model.fwarp = Softsplat()
     model.fwarp_max = Softsplat_Max()
     model.fwarp_count = Softsplat_Count()
-    model.forward = types.MethodType(forward_b200, model)
+    # forward is replaced at CLASS level (a one-off subclass of the instance's own class): a bound method stored on the
+    # instance would be copied into DataParallel replicas still bound to the device-0 module (VideoSR_base_model.py:36).
+    cls = type(model)
+    if not getattr(cls, "_motif_patched", False):
+        model.__class__ = type(cls.__name__, (cls,), {"forward": forward_b200, "_motif_patched": True, "__module__": cls.__module__})
     return model
 
 

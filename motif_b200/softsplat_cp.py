@@ -22,16 +22,10 @@ import torch.nn as nn
 
 from . import _lib
 
-_workspaces = {}
-
-
 def _workspace(device, nbytes):
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    """Scratch of one call, from torch's caching allocator on the current stream (stream-ordered reuse is the
+    allocator's job; nothing is cached here, so short-lived streams leak nothing)."""
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
 
 
 def _splat(tenInput, tenFlow, tenMetric, mode, atomic=False):

@@ -27,8 +27,9 @@ from oracle import build_ref
 SO = os.path.join(build_ref.OUT_DIR, "ref_gpu_sm100a.so")
 
 # (tag, N, C, H, W): sum splat with the normaliser channel (C = 130 + 1), max / count (C = 1)
-SPLAT_SHAPES = [("adobe", 1, 131, 720, 1280), ("vimeo", 1, 131, 256, 448), ("small", 2, 6, 37, 52)]
-UNIT_SHAPES = [("adobe", 1, 1, 720, 1280), ("vimeo", 1, 1, 256, 448), ("small", 2, 1, 37, 52)]
+# x3p5 / uhdq: HR sizes of BASELINE configs 3 (630x1120) and of a quarter-area crop of config 4 (LR 270x480 -> 1080x1920)
+SPLAT_SHAPES = [("adobe", 1, 131, 720, 1280), ("vimeo", 1, 131, 256, 448), ("small", 2, 6, 37, 52), ("x3p5", 1, 131, 630, 1120), ("uhdq", 1, 131, 1080, 1920)]
+UNIT_SHAPES = [("adobe", 1, 1, 720, 1280), ("vimeo", 1, 1, 256, 448), ("small", 2, 1, 37, 52), ("x3p5", 1, 1, 630, 1120), ("uhdq", 1, 1, 1080, 1920)]
 # PWC-Net pyramid levels of a 720x1280 pair and a small case
 CORR_SHAPES = [("l2", 1, 32, 192, 320), ("l3", 1, 64, 96, 160), ("l6", 1, 196, 12, 20), ("small", 2, 16, 12, 20)]
 

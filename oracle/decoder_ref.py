@@ -113,26 +113,33 @@ def decode(
     params: Dict[str, torch.Tensor],
     local_ensemble: bool = False,
     return_intermediates: bool = False,
+    splat_ops=None,
 ):
-    """``Ours.py:659-858`` on the CPU.  Returns ``(rgb [N,B,3,HH,WW], flow_out [2BN,2,HH,WW])``."""
+    """``Ours.py:659-858`` on the CPU.  Returns ``(rgb [N,B,3,HH,WW], flow_out [2BN,2,HH,WW])``.
+
+    The same torch operators run on CUDA tensors when the inputs live there (``oracle/decoder_ref_gpu.py``: the
+    reference's eager GPU path, with ``splat_ops`` = the reference's own CUDA kernels); ``splat_ops`` defaults to the
+    CPU restatement of the three splats (``oracle/softsplat_ref.py``)."""
+    S_ = splat_ops if splat_ops is not None else S
     feat = feat.float()
     flow_feat = flow_feat.float()
     residual = residual.float()
-    target_t = target_t.float()
+    dev = feat.device
+    target_t = target_t.float().to(dev)
     B, N = target_t.shape
     H, W = feat.shape[-2:]
-    alpha = params["alpha"].float()
+    alpha = params["alpha"].float().to(dev)
 
     if local_ensemble:
         vx_lst, vy_lst = [-1, 1], [-1, 1]
     else:
         vx_lst, vy_lst = [0], [0]
 
-    hr_coord = make_coord((HH, WW)).unsqueeze(0)
+    hr_coord = make_coord((HH, WW)).unsqueeze(0).to(dev)  # built on the CPU, then moved (Ours.py:667-668, 677)
     eps_shift = 1e-6
     rx = 2 / H / 2
     ry = 2 / W / 2
-    feat_coord = make_coord((H, W), flatten=False).permute(2, 0, 1).unsqueeze(0).expand(1, 2, H, W)
+    feat_coord = make_coord((H, W), flatten=False).permute(2, 0, 1).unsqueeze(0).expand(1, 2, H, W).to(dev)
 
     preds, areas = [], []
     inter = {}
@@ -206,9 +213,9 @@ def decode(
     raw_flow = flow
     flow, z = flow[:, :-1] * 20.0 * (HH / H), (torch.relu(flow[:, -1].unsqueeze(1)) * alpha)
 
-    output, warped_z = S.function_softsplat(splat_in, flow, z, "softmax")
-    z_max = S.function_softsplat_max(z.exp(), flow)
-    count = S.function_softsplat_count(z, flow)
+    output, warped_z = S_.function_softsplat(splat_in, flow, z, "softmax")
+    z_max = S_.function_softsplat_max(z.exp(), flow)
+    count = S_.function_softsplat_count(z, flow)
     output = output.clone()
     warped_z = warped_z.clone()
     if return_intermediates:
@@ -293,7 +300,7 @@ def random_params(seed: int = 0, weight_gain: float = 1.0, alpha: float = -20.0,
 REALISTIC = dict(weight_gain=1.0, first_gain=4.0, alpha=-20.0, rgb_bias=0.5, rgb_gain=3.0, z_bias=0.03)
 
 
-def count_unstable_mask(flow_hr: torch.Tensor, B: int, N: int, eps: float = 2.5e-4) -> torch.Tensor:
+def count_unstable_mask(flow_hr: torch.Tensor, B: int, N: int, eps: float = 2.5e-4, splat_ops=None) -> torch.Tensor:
     """Destination pixels at which the REFERENCE FUNCTION ITSELF is discontinuous in the flow.
 
     The count splat (``softsplat_count_cp.py:25-50``) adds 1 to the four corners of
@@ -304,13 +311,14 @@ def count_unstable_mask(flow_hr: torch.Tensor, B: int, N: int, eps: float = 2.5e
     the reference differ by O(1e-2) in RGB at such pixels, so the 1e-3 gate is applied to the others.
     ``flow_hr`` is ``[2*B*N, 2, HH, WW]`` (reference-major); returns bool ``[N, B, 1, HH, WW]``.
     """
-    base = S.function_softsplat_count(flow_hr[:, :1], flow_hr)
+    S_ = splat_ops if splat_ops is not None else S
+    base = S_.function_softsplat_count(flow_hr[:, :1], flow_hr)
     bad = torch.zeros_like(base, dtype=torch.bool)
     for sx in (-eps, eps):
         for sy in (-eps, eps):
             f = flow_hr.clone()
             f[:, 0] += sx
             f[:, 1] += sy
-            bad |= S.function_softsplat_count(f[:, :1], f) != base
+            bad |= S_.function_softsplat_count(f[:, :1], f) != base
     HH, WW = bad.shape[-2:]
     return bad.reshape(2, B, N, 1, HH, WW).any(0).permute(1, 0, 2, 3, 4)

@@ -107,14 +107,14 @@ def _load_hot_params(model, params):
         sd[k].copy_(v)
 
 
-def decoder_case(name, lr_hw, scale, times, batch, use_raft, seed, gain, first_gain, alpha, ensemble=False):
+def decoder_case(name, lr_hw, scale, times, batch, use_raft, seed, gain, first_gain, alpha, ensemble=False, z_bias=0.03):
     model = ref_shims.build_reference_model(seed=seed, splat_backend="reference_kernels")
     model.local_ensemble = ensemble  # Ours.py:453 (False as shipped); True = the four-latent LIIF ensemble of Ours.py:660-663, 758-764
     if not use_raft:
         model.flow_predictor = _SmoothFlow(seed + 7, magnitude=3.0)
     if gain is not None:
         _load_hot_params(model, decoder_ref.random_params(seed=seed + 11, weight_gain=gain, first_gain=first_gain,
-                                                          alpha=alpha, rgb_bias=0.5, rgb_gain=3.0, z_bias=0.03))
+                                                          alpha=alpha, rgb_bias=0.5, rgb_gain=3.0, z_bias=z_bias))
     torch.manual_seed(seed + 1)
     h, w = lr_hw
     low = torch.rand(batch, 2, 3, max(h // 4, 2), max(w // 4, 2))
@@ -180,6 +180,16 @@ def raft_corr_case():
     _save("raft_corr", fmap1=fmap1, fmap2=fmap2, coords=coords, radius=np.array([r]), out=out)
 
 
+def regime_cases():
+    """Weight regimes SURVEY 8c asks for beyond the reference initialisation: alpha in {-1, +0.5}
+    (exp(z) not degenerate; alpha > 0 makes max-splat candidates exceed the 1.0 the output starts at, Ours.py:794, 834,
+    softsplat_max_cp.py:254) and O(1)-scaled SIREN hidden weights (gain 2 and 4: sine arguments up to ~100)."""
+    decoder_case("decoder_alpha_m1", (12, 16), 4, [0.3, 0.8], 1, False, seed=4, gain=1.0, first_gain=4.0, alpha=-1.0)
+    decoder_case("decoder_alpha_p05", (12, 16), 4, [0.3, 0.8], 1, False, seed=5, gain=1.0, first_gain=4.0, alpha=0.5, z_bias=0.6)
+    decoder_case("decoder_gain2", (12, 16), 4, [0.5], 1, False, seed=6, gain=2.0, first_gain=4.0, alpha=-1.0)
+    decoder_case("decoder_gain4", (12, 16), 4, [0.5], 1, False, seed=7, gain=4.0, first_gain=4.0, alpha=-1.0)
+
+
 def ensemble_case():
     # the reference's local_ensemble=True branch (four shifted latents, diagonally swapped area weights)
     decoder_case("decoder_ens_x3", (12, 16), 3, [0.4], 2, False, seed=3, gain=1.0, first_gain=4.0, alpha=-20.0, ensemble=True)
@@ -191,6 +201,9 @@ if __name__ == "__main__":
     if "--ensemble-only" in sys.argv:
         ensemble_case()
         raise SystemExit(0)
+    if "--regimes-only" in sys.argv:
+        regime_cases()
+        raise SystemExit(0)
     if "--raft-corr-only" in sys.argv:
         raft_corr_case()
         raise SystemExit(0)
@@ -200,5 +213,6 @@ if __name__ == "__main__":
     splat_cases()
     correlation_cases()
     decoder_cases()
+    regime_cases()
     front_cases()
     raft_corr_case()

@@ -49,15 +49,26 @@ def test_correlation_lane_order_small():
     assert (out - g["out"]).abs().max().item() < 1e-6
 
 
-@pytest.mark.parametrize("case", ["decoder_raft", "decoder_x4", "decoder_x3p5_b2"])
+@pytest.mark.parametrize("case", ["decoder_raft", "decoder_x4", "decoder_x3p5_b2", "decoder_alpha_m1", "decoder_alpha_p05", "decoder_gain2", "decoder_gain4"])
 def test_decoder_oracle_reproduces_reference_forward(case):
     g = load_golden(case)
     HH, WW = [int(v) for v in g["hr_size"]]
     rgb, flow = decoder_ref.decode(g["feat"], g["flow_feat"], g["residual"], g["target_t"], HH, WW, hot_params(g))
     assert rgb.shape == g["out"].shape and flow.shape == g["flow_out"].shape
-    # bit-exact on the machine that generated the vectors; other CPUs may pick other GEMM/sin kernels
-    assert (rgb - g["out"]).abs().max().item() < 2e-5
+    # bit-exact on the machine that generated the vectors; other CPUs may pick other GEMM/sin kernels -- and at SIREN gain 4
+    # the fp32 function itself amplifies a one-ulp difference to 2e-2 in RGB (tests/test_decoder_fullsize_gpu.py measures it)
+    tol = 5e-2 if case == "decoder_gain4" else (2e-4 if case == "decoder_gain2" else 2e-5)
+    assert (rgb - g["out"]).abs().max().item() < tol
     assert (flow - g["flow_out"]).abs().max().item() < 2e-5
+
+
+def test_alpha_positive_golden_exercises_the_max_splat():
+    """alpha = +0.5: exp(z) > 1, so the max splat (softsplat_max_cp.py:254: output starts at 1.0) and the `zmax` synth_net
+    input (Ours.py:834) leave 1.0 -- the branch every alpha = -20 fixture leaves untouched."""
+    g = load_golden("decoder_alpha_p05")
+    HH, WW = [int(v) for v in g["hr_size"]]
+    _, _, inter = decoder_ref.decode(g["feat"], g["flow_feat"], g["residual"], g["target_t"], HH, WW, hot_params(g), return_intermediates=True)
+    assert inter["splat_max"].max().item() > 1.2 and (inter["splat_max"] > 1.0).float().mean().item() > 0.05
 
 
 def test_decoder_oracle_local_ensemble_reproduces_reference_forward():
