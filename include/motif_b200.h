@@ -201,6 +201,9 @@ int motif_tc_set_trace(long long* buf, int capacity);
  * out[1] = cycles spent issuing. */
 int motif_tc_mma_rate(long long* out, int n, int reps, int a_in_tmem, int n_acc, void* stream);
 int motif_tc_selftest(const float* x, const float* w, float* d, float* scratch, int terms, void* stream);
+/* Debug aid: host pointer to a 4 KB device-mapped buffer that expired mbarrier waits of the f16x3 decoder kernels report
+ * into before they trap (word 0 = count, then (barrier shared address, parity, block, thread) from word 4 on). */
+unsigned int* motif_tc_wait_debug_buffer(void);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ EXPORTS = [
     "motif_tc_selftest",
     "motif_tc_set_trace",
     "motif_tc_mma_rate",
+    "motif_tc_wait_debug_buffer",
 ]
 
 SPLAT_MODES = {"summation": 0, "average": 1, "linear": 2, "softmax": 3}
@@ -123,6 +124,7 @@ def _declare(lib):
     lib.motif_tc_mma_rate.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_tc_selftest.restype = c_int
     lib.motif_tc_selftest.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    lib.motif_tc_wait_debug_buffer.restype = POINTER(ctypes.c_uint)
     lib.motif_decode.restype = c_int
     lib.motif_decode.argtypes = [POINTER(DecodeT), c_void_p]
 

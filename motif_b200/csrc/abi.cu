@@ -92,3 +92,17 @@ extern "C" int motif_tc_set_trace(long long* buf, int capacity) {
   if (int rc = tc_set_trace(buf, capacity)) return rc;
   return f16_set_trace(buf, capacity);
 }
+
+// Debug aid: returns a host pointer to a 4 KB buffer mapped into the device (allocated on first use) that expired mbarrier
+// waits of the f16x3 decoder kernels report into: word 0 = number of reports, then (barrier shared address, parity, block,
+// thread) per report from word 4 on.  Host memory survives the trap that follows an expired wait.
+extern "C" unsigned int* motif_tc_wait_debug_buffer(void) {
+  static unsigned int* host = nullptr;
+  if (host == nullptr) {
+    if (cudaHostAlloc((void**)&host, 4096, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(host, 0, 4096);
+    unsigned int* dev = nullptr;
+    if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess || f16_set_wait_debug(dev) != 0) return nullptr;
+  }
+  return host;
+}

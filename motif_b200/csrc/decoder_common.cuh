@@ -142,5 +142,6 @@ int check_decode(const motif_decode_t* a);
 size_t tc_image_bytes();
 int tc_set_trace(long long* buf, int capacity);
 int f16_set_trace(long long* buf, int capacity);
+int f16_set_wait_debug(unsigned int* mapped);
 
 }  // namespace motif

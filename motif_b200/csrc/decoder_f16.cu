@@ -1600,6 +1600,12 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
 
 }  // namespace f16
 
+// Debug aid (tools/debug_waits.py): host-mapped buffer that expired mbarrier waits of this translation unit report into.
+int f16_set_wait_debug(unsigned int* mapped) {
+  MOTIF_CUDA(cudaMemcpyToSymbol(tc::g_wait_dbg, &mapped, sizeof(mapped)));
+  return 0;
+}
+
 int f16_set_trace(long long* buf, int capacity) {
 #ifdef MOTIF_TRACE
   int zero = 0;

@@ -48,10 +48,26 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spins until the phase with the given parity has completed.  A bounded spin turns a protocol bug into a
-// trap (reported as a CUDA error) instead of a hung GPU.
+// trap (reported as a CUDA error) instead of a hung GPU.  Debug aid: when a host-mapped buffer has been installed
+// (motif_tc_set_wait_debug), a thread whose wait expires first records (barrier address, parity, block, thread) there --
+// host memory survives the trap -- and keeps waiting a little longer so that the other stuck threads can record too.
+static __device__ unsigned int* g_wait_dbg = nullptr;  // per translation unit
+static __device__ __noinline__ void mbar_wait_expired(uint64_t* bar, uint32_t parity) {
+  if (g_wait_dbg != nullptr) {
+    const unsigned int i = atomicAdd(g_wait_dbg, 1u);
+    if (i < 255u) {
+      g_wait_dbg[4 + 4 * i] = smem_u32(bar);
+      g_wait_dbg[5 + 4 * i] = parity;
+      g_wait_dbg[6 + 4 * i] = blockIdx.x;
+      g_wait_dbg[7 + 4 * i] = threadIdx.x;
+    }
+    __threadfence_system();
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-    if (it > (1u << 20)) __trap();
+    if (it == (1u << 20)) mbar_wait_expired(bar, parity);
+    if (it > (1u << 20) + (1u << 16)) __trap();
   }
 }
 
@@ -176,6 +192,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 // Byte offset of element (row, k) of a [rows x 64] fp16 K-major operand block: one 128-byte row per matrix row
 // (all 64 k), 8-row swizzle atoms of 1024 bytes, 16-byte chunk index XOR row%8.

@@ -320,5 +320,18 @@ def count_unstable_mask(flow_hr: torch.Tensor, B: int, N: int, eps: float = 2.5e
             f[:, 0] += sx
             f[:, 1] += sy
             bad |= S_.function_softsplat_count(f[:, :1], f) != base
-    HH, WW = bad.shape[-2:]
+    # The joint shifts above can cancel (one source leaves a destination while another enters it).  Per source: a source
+    # that lands within eps of an integer grid line can move its unit of count between the destinations of the 3 x 3
+    # neighbourhood of its rounded landing position, whatever the other sources do.
+    n, _, HH, WW = flow_hr.shape
+    dev = flow_hr.device
+    px = torch.arange(WW, dtype=torch.float32, device=dev).view(1, 1, WW) + flow_hr[:, 0]
+    py = torch.arange(HH, dtype=torch.float32, device=dev).view(1, HH, 1) + flow_hr[:, 1]
+    rx, ry = torch.round(px), torch.round(py)
+    near = ((px - rx).abs() < eps) | ((py - ry).abs() < eps)
+    near &= (rx >= -1) & (rx <= WW) & (ry >= -1) & (ry <= HH)
+    idx = (ry.clamp(0, HH - 1) * WW + rx.clamp(0, WW - 1)).long()
+    hit = torch.zeros(n, HH * WW, dtype=torch.float32, device=dev)
+    hit.scatter_add_(1, idx.view(n, -1), near.view(n, -1).float())
+    bad |= F.max_pool2d(hit.view(n, 1, HH, WW), 3, stride=1, padding=1) > 0
     return bad.reshape(2, B, N, 1, HH, WW).any(0).permute(1, 0, 2, 3, 4)

@@ -59,7 +59,9 @@ def decode(feat, flow_feat, residual, target_t, HH, WW, params, chunk: int = 0):
     """Reference eager GPU forward of the hot path.  ``chunk`` > 0 decodes that many timestamps per pass, re-running the
     clip-invariant part each time -- exactly what ``VideoSRBaseModel.test`` does with chunks of three
     (``VideoSR_base_model.py:188-193``) -- which also bounds memory; 0 = all timestamps in one pass.
-    Returns ``(rgb [N,B,3,HH,WW], flow_out [2BN,2,HH,WW], flow_hr [2BN,2,HH,WW])`` on the device."""
+    Returns ``(rgb [N,B,3,HH,WW], flow_out [2BN,2,HH,WW], aux)`` on the device; ``aux['flow_hr'] [2BN,2,HH,WW]`` are the HR
+    flows and ``aux['wz'] [N,B,1,HH,WW]`` the blended normaliser ``W_0 + W_1`` (``Ours.py:812``) the discontinuity masks of
+    the parity tests are built from."""
     dev = feat.device
     assert dev.type == "cuda"
     p = {k: v.to(dev) for k, v in params.items()}
@@ -68,20 +70,34 @@ def decode(feat, flow_feat, residual, target_t, HH, WW, params, chunk: int = 0):
     torch.backends.cuda.matmul.allow_tf32 = False  # the reference runs plain fp32 (torch default)
     try:
         with torch.no_grad():
-            if chunk <= 0 or chunk >= N:
-                rgb, flow_out, inter = decoder_ref.decode(feat, flow_feat, residual, target_t, HH, WW, p, return_intermediates=True, splat_ops=RefKernelSplats)
-                return rgb, flow_out, inter["flow_hr"]
-            rgbs, fos, fhs = [], [], []
-            for n0 in range(0, N, chunk):
-                r, fo, inter = decoder_ref.decode(feat, flow_feat, residual, target_t[:, n0:n0 + chunk], HH, WW, p, return_intermediates=True, splat_ops=RefKernelSplats)
+            rgbs, fos, fhs, wzs = [], [], [], []
+            step = N if chunk <= 0 else chunk
+            for n0 in range(0, N, step):
+                r, fo, inter = decoder_ref.decode(feat, flow_feat, residual, target_t[:, n0:n0 + step], HH, WW, p, return_intermediates=True, splat_ops=RefKernelSplats)
                 n = r.shape[0]
                 rgbs.append(r)
                 fos.append(fo.reshape(2 * B, n, 2, HH, WW))
                 fhs.append(inter["flow_hr"].reshape(2 * B, n, 2, HH, WW))
+                wzs.append(inter["splat_norm"].reshape(2, B, n, 1, HH, WW).sum(0).permute(1, 0, 2, 3, 4))
                 del inter
-            return torch.cat(rgbs, 0), torch.cat(fos, 1).reshape(2 * B * N, 2, HH, WW), torch.cat(fhs, 1).reshape(2 * B * N, 2, HH, WW)
+            aux = {"flow_hr": torch.cat(fhs, 1).reshape(2 * B * N, 2, HH, WW), "wz": torch.cat(wzs, 0)}
+            return torch.cat(rgbs, 0), torch.cat(fos, 1).reshape(2 * B * N, 2, HH, WW), aux
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def equality_unstable_mask(wz: torch.Tensor, alpha: float = 0.0, z_err: float = 0.0, ulps: int = 8) -> torch.Tensor:
+    """Destinations at which the reference's exact-equality tests on the blended normaliser are undecided by rounding.
+
+    ``Ours.py:813`` replaces ``Wz == 0`` by 1 and ``:829`` replaces ``Wz == 1.0`` by 0 before forming the ``Wz / count``
+    input of ``synth_net`` (``:834``).  ``Wz`` is a sum of float ``atomicAdd``s (``softsplat_cp.py:40-51``) of
+    ``exp(relu(z_raw) * alpha) * w``: wherever the flow is locally a translation and ``z_raw <= 0`` the terms add up to
+    1 +- a few ulp in an order the hardware picks, and a term whose ``z_raw`` is within the evaluation error ``z_err`` of the
+    relu kink contributes ``exp(alpha * z_err) - 1`` more or less -- so two correct evaluations land on different sides of
+    the ``== 1.0`` test, ``Wz / count`` jumps between ``1 / count`` and 0 and RGB moves by O(1e-2).  The excluded set is
+    ``|Wz - 1| <= ulps * 2^-23 + 4 * |alpha| * z_err`` (and ``|Wz|`` tiny).  ``wz`` ``[N,B,1,HH,WW]``; returns bool."""
+    eps = ulps * 2.0 ** -23 + 4.0 * abs(alpha) * z_err
+    return ((wz - 1.0).abs() <= eps) | (wz.abs() <= ulps * 2.0 ** -23 * 1e-3)
 
 
 def count_unstable_mask(flow_hr, B, N, eps: float = 2.5e-4):

@@ -17,7 +17,7 @@ def _compare_frames(rgb, ref_rgb, ref_flow_out, scale_hh_over_h, B, N):
     oracle.decoder_ref.count_unstable_mask), PSNR over the same pixels, and the excluded fraction."""
     unstable = decoder_ref.count_unstable_mask(ref_flow_out * 20.0 * scale_hh_over_h, B, N).expand_as(ref_rgb)
     frac = unstable.float().mean().item()
-    assert frac < 0.01, frac
+    assert frac < 0.03, frac
     d = (rgb - ref_rgb).abs()
     a = torch.where(unstable, ref_rgb, rgb)
     return d[~unstable].max().item(), psnr(a, ref_rgb), frac

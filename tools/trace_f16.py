@@ -37,5 +37,7 @@ print(f"iterations of tile 0: {len(starts)}; mean period {(ts[starts[-1]] - ts[s
 first = int(os.environ.get("TRACE_FIRST", "10"))
 n_it = int(os.environ.get("TRACE_ITERS", "2"))
 a, b = starts[first], starts[first + n_it]
+skip = (lambda e: 1000 <= e < 3000) if os.environ.get("TRACE_NO_ISSUER") else (lambda e: False)
 for i in range(a, b):
-    print(f"   +{ts[i] - ts[a]:7d}  id {ids[i]}")
+    if not skip(ids[i]):
+        print(f"   +{ts[i] - ts[a]:7d}  id {ids[i]}")
