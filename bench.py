@@ -156,9 +156,11 @@ def main():
     H, W, HH, WW, times = synthetic.WORKLOADS[args.workload]
     B, N = 1, len(times)
     qs = HH * WW
+    HALO = 16  # source halo (HR rows) of a destination row band; checked against the largest |flow_y| after the timed loops
     config = {"workload": f"{args.workload}: LR {H}x{W} -> HR {HH}x{WW}, {N} timestamps, B=1, synthetic latents + synthetic best.pth-layout weights",
               "l2": "per-step working set (per-source rows 472 MB + destination lists 118 MB + frames 77 MB) >> 126 MB L2; no explicit flush",
-              "parallelism": f"timestamps sharded over {world} rank(s), NCCL broadcast of LR latents per step" if world > 1 else "single GPU"}
+              "parallelism": (f"destination row bands (+{HALO}-row source halo, verified) over {world} ranks, every rank all {N} timestamps; NCCL broadcast of the "
+                              "LR latents per step on a side stream, overlapped with the previous step's decode") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
         # The reference's CPU implementation of the path (oracle port), all host threads, rank 0 only.  Every step is a
@@ -201,15 +203,20 @@ def main():
     else:
         feat, ff, res = [torch.empty_like(t, device=dev) for t in (feat_h, ff_h, res_h)]
     tt = torch.tensor([times])
-    ranges = sharding.partition_timestamps(N, world)
-    n0, n1 = ranges[rank]
-    out_h = torch.empty(max(n1 - n0, 1), B, 3, HH, WW, dtype=torch.float32).pin_memory()
+    # N > 1: the second sharding axis of SURVEY 8e -- every rank decodes a band of destination rows of ALL timestamps (7
+    # timestamps do not divide over 2 / 4 / 8 ranks, and imnet / the LR tables would be replicated); N == 1: the whole frame
+    n0, n1 = 0, N
+    r0, r1 = sharding.partition_rows(HH, world)[rank] if world > 1 else (0, HH)
+    band = {"row_range": (r0, r1), "halo": HALO} if world > 1 else {}
+    out_h = torch.empty(N, B, 3, max(r1 - r0, 1), WW, dtype=torch.float32).pin_memory()
+    stat = torch.zeros(64, dtype=torch.float32, device=dev)
 
     from motif_b200.clip_stream import ClipStream
 
     stream = ClipStream(dec, depth=2, distributed=world > 1, src=0, return_flow=True)
     lat_shapes = tuple(tuple(t.shape) for t in (feat_h, ff_h, res_h))
     rgb_dev = torch.empty(N, B, 3, HH, WW, dtype=torch.float32, device=dev)
+    exchange = sharding.LatentExchange(lat_shapes, dev, src=0) if world > 1 else None
 
     def step(from_host: bool):
         """One clip.  Resident arm: latents already in HBM on rank 0 (broadcast + decode only).  Host arm (e2e): the
@@ -217,19 +224,25 @@ def main():
         neighbouring clips' decode (motif_b200/clip_stream.py); every clip's copies happen inside the timed region."""
         if from_host:
             if rank == 0:
-                stream.submit(feat_h, ff_h, res_h, tt, (HH, WW), out_h, n_range=(n0, n1))
+                stream.submit(feat_h, ff_h, res_h, tt, (HH, WW), out_h, n_range=(n0, n1), **band)
             else:
-                stream.submit(None, None, None, tt, (HH, WW), out_h, n_range=(n0, n1), shapes=lat_shapes)
+                stream.submit(None, None, None, tt, (HH, WW), out_h, n_range=(n0, n1), shapes=lat_shapes, **band)
             return
         if world > 1:
-            f2, g2, r2 = sharding.broadcast_latents(feat, ff, res, src=0)
+            f2, g2, r2 = exchange.take()                       # this step's broadcast (started during the previous step)
+            exchange.start((feat, ff, res) if rank == 0 else None)   # next step's, behind this step's decode
         else:
             f2, g2, r2 = feat, ff, res
-        dec.decode(f2, g2, r2, tt, (HH, WW), n_range=(n0, n1), return_flow=True, out=rgb_dev)  # both outputs of the forward (Ours.py:858)
+        if r1 > r0:
+            dec.decode(f2, g2, r2, tt, (HH, WW), n_range=(n0, n1), return_flow=True, out=rgb_dev, flow_y_max=stat if world > 1 else None, **band)  # both outputs of the forward (Ours.py:858)
+        if world > 1:
+            exchange.release()
 
     def timed(from_host: bool, steps: int, profile: bool):
         if world > 1:
             dist.barrier()
+            if not from_host:
+                exchange.start((feat, ff, res) if rank == 0 else None)   # prime the pipeline: the timed region does `steps` broadcasts
         torch.cuda.synchronize()
         if profile:
             _lib.prof_enable(True)
@@ -242,6 +255,10 @@ def main():
             torch.cuda.current_stream().wait_stream(stream.s_out)
         e1.record()
         torch.cuda.synchronize()
+        if world > 1 and not from_host:
+            exchange.take()   # drain the broadcast started by the last step (outside the timed region: it belongs to the next clip)
+            exchange.release()
+            torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = lib.motif_launch_count()
         if world > 1:
@@ -251,8 +268,13 @@ def main():
             dist.barrier()
         return ms, launches
 
+    if world > 1:
+        exchange.start((feat, ff, res) if rank == 0 else None)
     for _ in range(max(args.warmup, 3)):
         step(False)
+    if world > 1:
+        exchange.take()
+        exchange.release()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -271,6 +293,12 @@ def main():
     ms_e2e, _ = timed(True, args.steps, profile=False)
     stream.synchronize()
 
+    halo_check = None
+    if world > 1:  # the band decodes were exact iff no source moved farther than the halo allows
+        fy_resident = sharding.check_halo(stat, HALO)
+        fy_host = sharding.check_halo(stream.flow_y_max, HALO)
+        assert max(fy_resident, fy_host) < HALO - 1, f"source halo of {HALO} rows violated: max |flow_y| = {max(fy_resident, fy_host)}"
+        halo_check = {"halo_rows": HALO, "max_abs_flow_y_px": max(fy_resident, fy_host)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -281,7 +309,7 @@ def main():
     value = units_per_step * args.steps / (ms * 1e-3)
     e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
     h2d = (feat_h.numel() + ff_h.numel() + res_h.numel()) * 4
-    d2h = N * B * 3 * qs * 4
+    d2h = N * B * 3 * qs * 4  # all ranks together (each copies its own rows out)
 
     # ---- roofline of the dominant kernel of the step (per launch, CUDA events on the launch stream) ----
     # Algorithmic work per launch.  Tensor-bound kernels: dense MACs of the reference's layers
@@ -315,7 +343,7 @@ def main():
         avg = tot_ms / cnt
         bound, amount = work[k]
         if k not in per_clip:  # `work` is per timestamp; a launch covers a group of timestamps (f16x3: all of this rank's)
-            amount = amount * (n1 - n0) * args.steps / cnt
+            amount = amount * (n1 - n0) * args.steps / cnt * ((r1 - r0) / HH)  # this rank's rows
         rate = amount / (avg * 1e-3) / (1e12 if bound == "tensor" else 1e9)
         peak = tensor_peak if bound == "tensor" else peaks["hbm_gbs"]
         kernels[k] = {"launches_per_step": cnt / args.steps, "avg_ms": avg, "share_of_step": tot_ms / ms, "bound": bound,
@@ -379,7 +407,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                 "api": "ClipStream.submit: copy-in, decode and copy-out of consecutive clips overlap on three streams (depth 2); every clip's own copies are inside the timed region"},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "halo_check": halo_check,
         "roofline": roofline, "roofline_splat": roofline_splat, "kernels": kernels,
         "cpu_baseline": cpu_baseline,
     }

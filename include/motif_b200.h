@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MOTIF_ABI_VERSION 3
+#define MOTIF_ABI_VERSION 4
 
 #define MOTIF_E_BADARG (-1)   /* null pointer, non-positive size, unknown mode        */
 #define MOTIF_E_WORKSPACE (-2) /* workspace smaller than the *_workspace_bytes() answer */
@@ -175,6 +175,14 @@ typedef struct {
   int local_ensemble;  /* LunaTokis.local_ensemble (Ours.py:453, 660-663, 754-764): 0 as shipped = one nearest latent;
                         * 1 = the four shifted latents blended by diagonally swapped area weights.  Implemented by
                         * MOTIF_PRECISION_FP32 only (other precisions return MOTIF_E_UNSUPPORTED).       */
+  /* Destination row band of a sharded decode (MOTIF_PRECISION_F16X3 only).  row_end == 0: the whole image.
+   * Otherwise only the destination rows [row_begin, row_end) of `rgb` are produced (row_begin and row_end multiples of 8, or
+   * row_end == HH) and only the sources of rows [row_begin - halo, row_end + halo) are evaluated (`flow_out` is written for
+   * those rows only): correct iff no source outside them lands inside the band, i.e. iff max |flow_y| < halo - 1 HR pixels
+   * everywhere.  flow_y_max (device, 64 words, may be NULL) receives the float bit patterns whose maximum is the largest
+   * |flow_y| over the sources of the band's OWN rows; the maximum over all bands of a clip checks the halo. */
+  int row_begin, row_end, halo;
+  float* flow_y_max;
   int weights_ready;   /* 1: `workspace` still holds the weight images a previous motif_decode wrote for THESE weights at THIS
                         * precision (same workspace pointer, nothing else wrote to it): the per-call repacking is skipped.
                         * Honoured by MOTIF_PRECISION_F16X3; 0 is always safe.                                          */
@@ -187,6 +195,8 @@ typedef struct {
 enum { MOTIF_PRECISION_TF32X3 = 0, MOTIF_PRECISION_FP32 = 1, MOTIF_PRECISION_F16X3 = 2 };
 
 size_t motif_decode_workspace_bytes(int B, int N, int H, int W, int HH, int WW);
+/* sizeof(motif_decode_t) as this library was compiled: lets a foreign-language binding verify its struct layout. */
+size_t motif_sizeof_decode_t(void);
 /* Whole hot path for one batch of clips from resident LR latents: imnet once per clip, then
  * per timestamp flow_imnet -> 3 splats of both references -> blend -> synth_net -> clamp. */
 int motif_decode(const motif_decode_t* args, void* stream);

@@ -34,6 +34,7 @@ EXPORTS = [
     "motif_query_geometry",
     "motif_pack_latents",
     "motif_decode_workspace_bytes",
+    "motif_sizeof_decode_t",
     "motif_decode",
     "motif_tc_selftest",
     "motif_tc_set_trace",
@@ -78,6 +79,8 @@ class DecodeT(Structure):
         ("n_begin", c_int), ("n_end", c_int),
         ("precision", c_int),
         ("local_ensemble", c_int),
+        ("row_begin", c_int), ("row_end", c_int), ("halo", c_int),
+        ("flow_y_max", c_void_p),
         ("weights_ready", c_int),
     ]
 
@@ -118,6 +121,7 @@ def _declare(lib):
     lib.motif_pack_latents.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_decode_workspace_bytes.restype = c_size_t
     lib.motif_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.motif_sizeof_decode_t.restype = c_size_t
     lib.motif_tc_set_trace.restype = c_int
     lib.motif_tc_set_trace.argtypes = [c_void_p, c_int]
     lib.motif_tc_mma_rate.restype = c_int

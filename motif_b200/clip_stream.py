@@ -3,14 +3,16 @@
 ``SpaceTimeDecoder.decode`` works on resident device tensors.  A caller that holds the LR latents in
 host memory (the encoder ran elsewhere, or clips are streamed from disk) pays a host->device copy
 of 320*H*W*4 bytes and a device->host copy of 12 bytes per output pixel-timestamp per clip -- at
-Adobe240 size 1.4 ms each way over PCIe against ~7 ms of decode.  ``ClipStream`` overlaps them
+Adobe240 size 1.4 ms each way over PCIe against ~6 ms of decode.  ``ClipStream`` overlaps them
 with the decode of the neighbouring clips: three CUDA streams (copy-in, compute, copy-out), two
 sets of device buffers, events between them.  Every clip's copies are issued by ``submit`` itself
 (nothing is cached across clips); ``synchronize`` waits for everything submitted so far.
 
 With ``torch.distributed`` initialised and ``world_size > 1`` the source rank copies the latents
-in and they are broadcast (the path's one exchange, ``sharding.broadcast_latents``) on the compute
-stream of every rank before its timestamps are decoded.
+in and broadcasts them (the path's one exchange) ON THE COPY-IN STREAM, i.e. behind the decode of the
+previous clip; every rank then decodes its share -- a range of timestamps (``n_range``), a band of
+destination rows with a source halo (``row_range`` / ``halo``), or both -- and copies only
+that share out.
 """
 from __future__ import annotations
 
@@ -18,7 +20,6 @@ from typing import Optional, Sequence, Tuple
 
 import torch
 
-from . import sharding
 from .decoder import SpaceTimeDecoder
 
 
@@ -37,6 +38,7 @@ class ClipStream:
         self.s_out = torch.cuda.Stream(self.dev)
         self._slots = [None] * depth
         self._k = 0
+        self.flow_y_max = torch.zeros(64, dtype=torch.float32, device=self.dev)  # of the last band decode (sharding.check_halo)
 
     def _slot(self, k, shapes, out_shape):
         i = k % self.depth
@@ -45,11 +47,11 @@ class ClipStream:
             if sl is not None:
                 # the old buffers may still be the target / source of copies in flight on the side streams: tell the
                 # caching allocator (they were allocated on the compute stream) before dropping them
-                for t in sl["lat"]:
-                    t.record_stream(self.s_in)
+                sl["flat"].record_stream(self.s_in)
                 sl["out"].record_stream(self.s_out)
-            sl = {"shapes": shapes,
-                  "lat": [torch.empty(s, dtype=torch.float32, device=self.dev) for s in shapes],
+            sizes = [int(torch.Size(s).numel()) for s in shapes]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.dev)
+            sl = {"shapes": shapes, "flat": flat, "lat": [p.view(s) for p, s in zip(torch.split(flat, sizes), shapes)],
                   "out": torch.empty(out_shape, dtype=torch.float32, device=self.dev),
                   "ev_in": torch.cuda.Event(), "ev_free": None, "ev_done": torch.cuda.Event(), "ev_out": None}
             self._slots[i] = sl
@@ -57,11 +59,11 @@ class ClipStream:
 
     def submit(self, feat_h: Optional[torch.Tensor], flow_feat_h: Optional[torch.Tensor], residual_h: Optional[torch.Tensor],
                target_t, hr_size: Tuple[int, int], out_h: Optional[torch.Tensor], n_range: Optional[Tuple[int, int]] = None,
-               shapes: Optional[Sequence[Tuple[int, ...]]] = None):
+               shapes: Optional[Sequence[Tuple[int, ...]]] = None, row_range: Optional[Tuple[int, int]] = None, halo: int = 0):
         """Queue one clip.  ``feat_h`` / ``flow_feat_h`` / ``residual_h``: pinned host tensors (on ranks other
         than ``src`` of a distributed stream pass ``None`` and the three ``shapes``).  ``out_h``: pinned host tensor
-        ``[n_end - n_begin, B, 3, HH, WW]`` receiving this rank's frames (or ``None`` to leave them on the device).
-        Returns the device frame buffer ``[N, B, 3, HH, WW]`` of this slot (valid until the slot is reused)."""
+        ``[n_end - n_begin, B, 3, r1 - r0, WW]`` receiving this rank's share of the frames (or ``None`` to leave them on the
+        device).  Returns the device frame buffer ``[N, B, 3, HH, WW]`` of this slot (valid until the slot is reused)."""
         import torch.distributed as dist
 
         is_src = (not self.distributed) or dist.get_rank(self.group) == self.src
@@ -74,29 +76,32 @@ class ClipStream:
         B, N = tt.shape
         HH, WW = int(hr_size[0]), int(hr_size[1])
         n0, n1 = (0, N) if n_range is None else n_range
+        r0, r1 = (0, HH) if row_range is None else row_range
         sl = self._slot(self._k, shapes, (N, B, 3, HH, WW))
         self._k += 1
         compute = torch.cuda.current_stream(self.dev)
-        if is_src:
-            with torch.cuda.stream(self.s_in):
-                if sl["ev_free"] is not None:
-                    self.s_in.wait_event(sl["ev_free"])        # the decode that last read these buffers has finished
+        with torch.cuda.stream(self.s_in):
+            if sl["ev_free"] is not None:
+                self.s_in.wait_event(sl["ev_free"])            # the decode that last read these buffers has finished
+            if is_src:
                 for dst, src_t in zip(sl["lat"], (feat_h, flow_feat_h, residual_h)):
                     dst.copy_(src_t, non_blocking=True)
-                sl["ev_in"].record(self.s_in)
-            compute.wait_event(sl["ev_in"])
+            if self.distributed:
+                dist.broadcast(sl["flat"], src=self.src, group=self.group)   # one flat buffer, no staging copy
+            sl["ev_in"].record(self.s_in)
+        compute.wait_event(sl["ev_in"])
         if sl["ev_out"] is not None:
             compute.wait_event(sl["ev_out"])                   # the copy-out that last read this frame buffer has finished
         lat = sl["lat"]
-        if self.distributed:
-            lat = sharding.broadcast_latents(*lat, src=self.src, group=self.group)
-        self.dec.decode(lat[0], lat[1], lat[2], tt, (HH, WW), n_range=(n0, n1), return_flow=self.return_flow, out=sl["out"])
+        band = {} if row_range is None else {"row_range": (r0, r1), "halo": halo, "flow_y_max": self.flow_y_max}
+        if n1 > n0 and r1 > r0:
+            self.dec.decode(lat[0], lat[1], lat[2], tt, (HH, WW), n_range=(n0, n1), return_flow=self.return_flow, out=sl["out"], **band)
         sl["ev_done"].record(compute)
         sl["ev_free"] = sl["ev_done"]
-        if out_h is not None and n1 > n0:
+        if out_h is not None and n1 > n0 and r1 > r0:
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(sl["ev_done"])
-                out_h[: n1 - n0].copy_(sl["out"][n0:n1], non_blocking=True)
+                out_h[: n1 - n0, :, :, : r1 - r0].copy_(sl["out"][n0:n1, :, :, r0:r1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.s_out)
                 sl["ev_out"] = ev

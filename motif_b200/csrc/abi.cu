@@ -72,6 +72,7 @@ extern "C" int motif_prof_collect(const char* const* names, int n_names, double*
 }
 
 extern "C" int motif_abi_version(void) { return MOTIF_ABI_VERSION; }
+extern "C" size_t motif_sizeof_decode_t(void) { return sizeof(motif_decode_t); }
 extern "C" const char* motif_last_error(void) { return g_last_error; }
 extern "C" long long motif_launch_count(void) { return g_launches.load(); }
 extern "C" void motif_reset_launch_count(void) { g_launches.store(0); }
@@ -80,6 +81,8 @@ extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
   if (int rc = check_decode(args)) return rc;
   if (args->local_ensemble != 0 && args->precision != MOTIF_PRECISION_FP32)
     return fail(MOTIF_E_UNSUPPORTED, "decode: local_ensemble is implemented by MOTIF_PRECISION_FP32 only (precision %d given)", args->precision);
+  if (args->row_end != 0 && args->precision != MOTIF_PRECISION_F16X3)
+    return fail(MOTIF_E_UNSUPPORTED, "decode: destination row bands are implemented by MOTIF_PRECISION_F16X3 only (precision %d given)", args->precision);
   switch (args->precision) {
     case MOTIF_PRECISION_TF32X3: return decode_tc(args, (cudaStream_t)stream);
     case MOTIF_PRECISION_FP32: return decode_simt(args, (cudaStream_t)stream);

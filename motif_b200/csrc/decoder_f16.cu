@@ -91,6 +91,16 @@ static int trace_select(int kernel, cudaStream_t st) {
 enum { kImgF1 = 0, kImgF2 = 1, kImgI1 = 5, kImgI2 = 6, kImgI3 = 10, kImgS1 = 14, kImgS2 = 15, kImgS3 = 16, kNumImg = 20 };
 enum { kScF1 = 0, kScF2, kScI1, kScI2, kScI3, kScS1, kScS2, kScS3, kNumSc };
 
+// Destination row band of a sharded decode: this call produces the destination rows [row_begin, row_end) of every
+// timestamp it is given and evaluates the sources of rows [src_begin, src_end) = the band widened by the halo (a source can only
+// land in the band if |flow_y| < halo - 1; the largest |flow_y| of the band's own sources is reported so that the caller can
+// check the halo).  The whole image is the band [0, HH) with src = [0, HH).
+struct Band {
+  int row_begin, row_end;  // destination rows (row_begin a multiple of 8)
+  int src_begin, src_end;  // source rows
+  unsigned int* flow_y_max;  // [64] float bit patterns (non-negative): max |flow_y| in HR pixels over the sources of the band's rows; may be null
+};
+
 constexpr int kMaxGroup = 8;  // timestamps decoded together (their lists, accumulators and A operands are all live)
 struct Times {
   float t[kMaxGroup];
@@ -673,12 +683,12 @@ using SmemI = Smem<9, 0>;
 
 // consts: [0,256) e0 float4 (30 b0, 30 w_rely, 30 w_relx, 0)  [256,320) 30 b1  [320,576) 30 b2  [576,640) 30 * folded bias
 //         [640] s1  [641] s2  [642] s3
-__global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, int B, int b, Scratch sc) {
+__global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, int B, int b, Scratch sc, int q_begin, int q_end) {
   extern __shared__ unsigned char smem_raw[];
   SmemI& sm = *reinterpret_cast<SmemI*>(align1024(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int n_tiles = (qs + 127) / 128;
+  const int n_tiles = (q_end - q_begin + 127) / 128;  // source pixels [q_begin, q_end) (whole rows of a band + halo)
   const int n_iters = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const float* wp = sc.wpack;
   for (int i = threadIdx.x; i < 64; i += blockDim.x) {
@@ -704,9 +714,9 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
     const float s1 = sm.consts[640], s2 = sm.consts[641], s3 = sm.consts[642];
     for (int it = 0; it < n_iters; ++it) {
       const int tile_id = blockIdx.x + it * gridDim.x;
-      const int q = tile_id * 128 + c.quad * 32 + lane;
-      const bool live = q < qs;
-      const int qc = live ? q : qs - 1;
+      const int q = q_begin + tile_id * 128 + c.quad * 32 + lane;
+      const bool live = q < q_end;
+      const int qc = live ? q : q_end - 1;
       const Query qu = make_query(qc / g.WW, qc % g.WW, g);
       const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
       table_layer0(c, sc.p0i + lr * 64, e0, qu.rel_y, qu.rel_x);
@@ -1041,6 +1051,7 @@ using QSmemF = QSmem<5>;
 // with them inlined ptxas has no uniform registers left for the output-layer constants and loads those per thread.
 struct ScatterCtx {
   int items_per_t, n0, B, b, N, qs, WW, HH;
+  int q_begin, q_end, row_begin, row_end;  // sources [q_begin, q_end) are evaluated; only destinations of rows [row_begin, row_end) are binned
   float flow_scale, alpha;
   float* flow_out;
   int* bin_count;
@@ -1055,8 +1066,8 @@ __device__ __noinline__ void scatter_item(const ScatterCtx& cx, int item, int ro
   const int nl = item / cx.items_per_t, rem = item - nl * cx.items_per_t;
   const int n = cx.n0 + nl;
   const int rb = (rem & 1) * cx.B + cx.b;
-  const int q = (rem >> 1) * 128 + row;
-  if (q >= qs) return;
+  const int q = cx.q_begin + (rem >> 1) * 128 + row;
+  if (q >= cx.q_end) return;
   const int qy = q / WW, qx = q - qy * WW;
   // Ours.py:794: flow = raw * 20. * (HH / H);  z = relu(raw_z) * alpha;  softsplat_cp.py:332: e = exp(z)
   const float fx = __fmul_rn(__fmul_rn(dx, 20.0f), cx.flow_scale);
@@ -1080,7 +1091,7 @@ __device__ __noinline__ void scatter_item(const ScatterCtx& cx, int item, int ro
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int cx_ = f.x0 + (k & 1), cy_ = f.y0 + (k >> 1);
-    ok[k] = !((cx_ < 0) | (cx_ >= WW) | (cy_ < 0) | (cy_ >= cx.HH));
+    ok[k] = !((cx_ < 0) | (cx_ >= WW) | (cy_ < cx.row_begin) | (cy_ >= cx.row_end));  // row_end <= HH: another band's destinations are its owner's
     dd[k] = dbase + (size_t)(ok[k] ? cy_ : 0) * WW + (ok[k] ? cx_ : 0);
     slot[k] = ok[k] ? atomicAdd(cx.bin_count + dd[k], 1) : 0;
   }
@@ -1111,18 +1122,20 @@ __device__ __noinline__ void scatter_item(const ScatterCtx& cx, int item, int ro
 //         [1348] s1 [1349] s2   [2048 + 256 nl, +256) e0 of timestamp nl, per pair of units (see q_table_layer0)
 // Work item = (timestamp of the group, reference frame, 128-pixel tile), timestamp-major.
 __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, float alpha, Scratch sc,
-                                                                float* __restrict__ flow_out) {
+                                                                float* __restrict__ flow_out, Band band) {
   extern __shared__ unsigned char smem_raw[];
   QSmemF& sm = *reinterpret_cast<QSmemF*>(align1024(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int items_per_t = 2 * ((qs + 127) / 128);
+  const int q_begin = band.src_begin * g.WW, q_end = band.src_end * g.WW;
+  const int items_per_t = 2 * ((q_end - q_begin + 127) / 128);
   const int n_items = nt * items_per_t;
   const float* wp = sc.wpack;
   __shared__ ScatterCtx s_ctx;
   if (threadIdx.x == 0) {
     s_ctx.items_per_t = items_per_t, s_ctx.n0 = n0, s_ctx.B = B, s_ctx.b = b, s_ctx.N = N, s_ctx.qs = qs, s_ctx.WW = g.WW, s_ctx.HH = g.HH;
     s_ctx.flow_scale = g.flow_scale, s_ctx.alpha = alpha, s_ctx.flow_out = flow_out;
+    s_ctx.q_begin = q_begin, s_ctx.q_end = q_end, s_ctx.row_begin = band.row_begin, s_ctx.row_end = band.row_end;
     s_ctx.bin_count = sc.bin_count, s_ctx.side = sc.side, s_ctx.zmax = sc.zmax, s_ctx.bin_ent = sc.bin_ent, s_ctx.Y = sc.Y, s_ctx.spill = sc.spill;
   }
   for (int i = threadIdx.x; i < 32 * nt; i += blockDim.x) {  // pair of units (2 pr, 2 pr + 1) of timestamp i / 32
@@ -1180,8 +1193,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       const int nl = item / items_per_t, rem = item - nl * items_per_t;
       const float4* e0 = reinterpret_cast<const float4*>(sm.consts + 2048 + 256 * nl);
       const int rb = (rem & 1) * B + b;
-      const int q = (rem >> 1) * 128 + row;
-      const int qc = q < qs ? q : qs - 1;
+      const int q = q_begin + (rem >> 1) * 128 + row;
+      const int qc = q < q_end ? q : q_end - 1;
       const int qy = qc / g.WW, qx = qc % g.WW;
       const Query qu = make_query(qy, qx, g);
       const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
@@ -1197,6 +1210,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
 #endif
       TRACE_Q(c, 2);
+      if (band.flow_y_max != nullptr) {  // halo check of a sharded decode: largest |flow_y| over the sources of the band's own rows
+        const bool own = (q < q_end) & (qy >= band.row_begin) & (qy < band.row_end);
+        const float fy = own ? fabsf(__fmul_rn(__fmul_rn(dy, 20.0f), g.flow_scale)) : 0.0f;
+        const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(fy == fy ? fy : 3.0e38f));
+        if (lane == 0 && m != 0u) atomicMax(band.flow_y_max + (blockIdx.x & 63), m);
+      }
       p_dx = dx, p_dy = dy, p_z = zraw, p_item = item;
     }
     if (p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
@@ -1239,14 +1258,18 @@ constexpr int kBandBlockRows = 4;  // block rows (of kGH destination rows) per L
 // (one LDG.128 per list entry and lane, a half-warp reads one 256-byte source row).  All rows of a destination
 // (first 8 entries, then the rare 9..16) are requested back to back before the first is used; slots past the list
 // length are predicated off, never zero-filled.
+// kBand: only `blocks_y_band` block rows of the image, starting at block blk0, are processed (a destination row band of a sharded
+// decode).  The whole-image instantiation is kept textually identical to the kernel this was tuned as: ptxas's schedule of
+// the body is fragile (the same body behind a slightly different prologue measured 2.57 instead of 2.04 ms).
+template <bool kBand>
 __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, Scratch sc,
-                                                          float* __restrict__ dbg_pre0, int band_rows) {
+                                                          float* __restrict__ dbg_pre0, int band_rows, int blk0, int blocks_y_band) {
   __shared__ uint2 ent_s[kGH][kGW][kSlots];  // the warp's 32 destination lists (4 KB per warp)
   __shared__ float4 par_s[kGH][kGW][2];      // per-destination scalars (1 KB per warp)
   __shared__ float4 rk_s[16][7];             // rank-1 layer-0 weights per 4-channel group (every warp writes the same values)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
   const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int blocks_x = (g.WW + kGW - 1) / kGW, blocks_y = (g.HH + kGH - 1) / kGH;
+  const int blocks_x = (g.WW + kGW - 1) / kGW, blocks_y = kBand ? blocks_y_band : (g.HH + kGH - 1) / kGH;
   int blk, nl;
   {
     const int per_band = band_rows * blocks_x;                  // blocks of one timestamp in a full band
@@ -1264,6 +1287,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
     }
   }
   const float t = time_of(times, nl);
+  if (kBand) blk += blk0;  // from here on the block's index in the whole image
   const int qy = (blk / blocks_x) * kGH + warp;
   const int x0 = (blk % blocks_x) * kGW;
   if (qy >= g.HH) return;  // whole warps only; no block-wide barrier below
@@ -1326,7 +1350,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
   const float4* Y4 = reinterpret_cast<const float4*>(sc.Y) + l16;
   const float4* R4 = reinterpret_cast<const float4*>(sc.rtab + (size_t)b * P * 64) + l16;
   const int bn = b * N + n0 + nl;
-  uint32_t* a0_out = sc.a0 + (((size_t)nl * B + b) * ((size_t)blocks_x * blocks_y) * (kGW * kGH) + ((size_t)blk * kGH + warp) * kGW) * 64;
+  uint32_t* a0_out = sc.a0 + (((size_t)nl * B + b) * ((size_t)blocks_x * (kBand ? (g.HH + kGH - 1) / kGH : blocks_y)) * (kGW * kGH) + ((size_t)blk * kGH + warp) * kGW) * 64;
 
 #ifndef MOTIF_GATHER_UNROLL
 #define MOTIF_GATHER_UNROLL 2  // two destinations pairs per trip: 2.06 -> 2.03 ms (12 bytes of spills at the 80-register cap)
@@ -1414,7 +1438,7 @@ using QSmemS = QSmem<6>;
 // consts: [0,64) 30 b1  [64,128) 30 b2  [128,1152) output weights per pair of hidden units (see q_sine_out3)  [1152,1155) b4
 //         [1156] s1  [1157] s2  [1158] s3
 // Work item = (timestamp of the group, 128 consecutive destinations in a-order), timestamp-major.
-__global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, int items_per_t, Scratch sc,
+__global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, int items_per_t, int items_img, int item0, Scratch sc,
                                                              float* __restrict__ rgb) {
   extern __shared__ unsigned char smem_raw[];
   QSmemS& sm = *reinterpret_cast<QSmemS*>(align1024(smem_raw));
@@ -1467,10 +1491,11 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
       TRACE_Q(c, 1);
       const int nl = item / items_per_t;
       const int n = n0 + nl;
-      const int a = (item - nl * items_per_t) * 128 + c.quad * 32 + lane;
+      // items_per_t items of this call per timestamp, starting at item0 of the items_img 128-destination runs of the whole image
+      const int a = (item0 + item - nl * items_per_t) * 128 + c.quad * 32 + lane;
       // layer-1 A operand: this row's 64 fp16 hi/lo pairs from the gather kernel
       {
-        const uint4* src = reinterpret_cast<const uint4*>(sc.a0) + (((size_t)nl * B + b) * items_per_t * 128 + a) * 16;
+        const uint4* src = reinterpret_cast<const uint4*>(sc.a0) + (((size_t)nl * B + b) * items_img * 128 + a) * 16;
         uint4 v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __ldg(src + k);
@@ -1651,9 +1676,11 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sq));
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 50));
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    const int carve = getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 50;
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
     MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -1673,13 +1700,29 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   mark_kernel<<<1, 32, 0, st>>>(sc.armed, none);
   MOTIF_LAUNCHED("mark_kernel");
   if (int rc = prepare(a, sc, st)) return rc;
-  const int tiles128 = ceil_div((long long)qs, 128);
+  // destination row band of a sharded decode (the whole image when row_end == 0): sources of the band widened by the halo
+  Band band;
+  band.row_begin = 0, band.row_end = g.HH, band.src_begin = 0, band.src_end = g.HH, band.flow_y_max = nullptr;
+  if (a->row_end > 0) {
+    MOTIF_REQUIRE(a->row_begin >= 0 && a->row_begin < a->row_end && a->row_end <= g.HH && a->row_begin % kGH == 0 && (a->row_end % kGH == 0 || a->row_end == g.HH) &&
+                      a->halo >= 0,
+                  "decode: bad destination row band [%d,%d) (multiples of %d inside [0,%d]) or halo %d", a->row_begin, a->row_end, kGH, g.HH, a->halo);
+    band.row_begin = a->row_begin, band.row_end = a->row_end;
+    band.src_begin = a->row_begin - a->halo > 0 ? a->row_begin - a->halo : 0;
+    band.src_end = a->row_end + a->halo < g.HH ? a->row_end + a->halo : g.HH;
+    band.flow_y_max = reinterpret_cast<unsigned int*>(a->flow_y_max);
+    if (band.flow_y_max != nullptr) MOTIF_CUDA(cudaMemsetAsync(band.flow_y_max, 0, 64 * sizeof(unsigned int), st));
+  }
+  const int q_begin = band.src_begin * g.WW, q_end = band.src_end * g.WW;
+  const int tiles128 = ceil_div((long long)(q_end - q_begin), 128);  // 128-pixel runs of source pixels
   const int grid128 = tiles128 < n_sm ? tiles128 : n_sm;
+  const int blocks_x = ceil_div(g.WW, kGW), by0 = band.row_begin / kGH, by1 = ceil_div(band.row_end, kGH);
+  const int band_blocks = (by1 - by0) * blocks_x;                    // 32 x 8 destination blocks of the band
   for (int b = 0; b < g.B; ++b) {
     {
       if (int rc = trace_select(0, st)) return rc;
       ProfScope prof("imnet_f16_kernel", st);
-      imnet_f16_kernel<<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc);
+      imnet_f16_kernel<<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc, q_begin, q_end);
       MOTIF_LAUNCHED("imnet_f16_kernel");
     }
     for (int n0 = a->n_begin; n0 < a->n_end; n0 += NT) {
@@ -1691,21 +1734,24 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
         if (int rc = trace_select(1, st)) return rc;
         ProfScope prof("flow_bin_f16_kernel", st);
         const int groups = ceil_div((long long)nt * 2 * tiles128, 4);
-        flow_bin_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n0, nt, b, times, a->alpha, sc, a->flow_out);
+        flow_bin_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n0, nt, b, times, a->alpha, sc, a->flow_out, band);
         MOTIF_LAUNCHED("flow_bin_f16_kernel");
       }
       {
         ProfScope prof("gather_l0_kernel", st);
         static const int band_rows = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : kBandBlockRows;
         static const int dsmem = getenv("MOTIF_GATHER_DSMEM") ? atoi(getenv("MOTIF_GATHER_DSMEM")) : 0;
-        gather_l0_kernel<<<nt * g_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows);
+        if (a->row_end > 0)
+          gather_l0_kernel<true><<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, by0 * blocks_x, by1 - by0);
+        else
+          gather_l0_kernel<false><<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, 0, 0);
         MOTIF_LAUNCHED("gather_l0_kernel");
       }
       {
         if (int rc = trace_select(2, st)) return rc;
         ProfScope prof("synth_f16_kernel", st);
-        const int items_per_t = 2 * g_blocks, groups = ceil_div((long long)nt * items_per_t, 4);
-        synth_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_sq, st>>>(g, g.B, g.N, n0, nt, b, items_per_t, sc, a->rgb);
+        const int items_per_t = 2 * band_blocks, groups = ceil_div((long long)nt * items_per_t, 4);
+        synth_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_sq, st>>>(g, g.B, g.N, n0, nt, b, items_per_t, 2 * g_blocks, 2 * by0 * blocks_x, sc, a->rgb);
         MOTIF_LAUNCHED("synth_f16_kernel");
       }
     }

@@ -168,11 +168,20 @@ class SpaceTimeDecoder:
         precision: Optional[str] = None,
         debug_pre0: bool = False,
         out: Optional[torch.Tensor] = None,
+        row_range: Optional[Tuple[int, int]] = None,
+        halo: int = 0,
+        flow_y_max: Optional[torch.Tensor] = None,
     ):
         """``Ours.py:659-858``.  Returns ``(rgb [N,B,3,HH,WW] in [0,1], flow_out [2BN,2,HH,WW] or None)``
         (plus the ``[B*N,198,HH,WW]`` synth_net input when ``debug_synth_in`` -- precisions ``fp32`` / ``tf32x3`` --
         or the ``[B*N,64,HH,WW]`` layer-0 pre-activation of synth_net when ``debug_pre0`` -- precision ``f16x3``,
-        which never forms the 198-channel input).  ``out``: optional preallocated frame buffer (``ClipStream``)."""
+        which never forms the 198-channel input).  ``out``: optional preallocated frame buffer (``ClipStream``).
+
+        ``row_range=(r0, r1)`` (multiples of 8, or ``r1 == HH``) decodes only the destination rows ``[r0, r1)`` of every
+        frame -- the other rows of ``rgb`` are left untouched -- from the sources of rows ``[r0 - halo, r1 + halo)``
+        (the second sharding axis).  Exact iff no source outside them lands in the band, i.e. iff
+        ``max |flow_y| < halo - 1`` HR pixels; ``flow_y_max`` (a 64-element fp32 CUDA tensor) receives values whose maximum is
+        the largest ``|flow_y|`` over the band's own source rows (``sharding.check_halo`` reduces it over the ranks)."""
         lib = _lib.load()
         for nm, t in (("feat", feat), ("flow_feat", flow_feat), ("residual", residual)):
             _lib.require_cuda_f32(nm, t, 4)
@@ -216,6 +225,12 @@ class SpaceTimeDecoder:
             a.n_begin, a.n_end = int(n0), int(n1)
             a.precision = PRECISIONS[precision or self.precision]
             a.local_ensemble = int(self.local_ensemble)
+            if row_range is not None:
+                a.row_begin, a.row_end, a.halo = int(row_range[0]), int(row_range[1]), int(halo)
+                if flow_y_max is not None:
+                    if flow_y_max.numel() != 64 or flow_y_max.dtype != torch.float32 or flow_y_max.device != residual.device:
+                        raise ValueError("flow_y_max must be a 64-element fp32 tensor on the decode device")
+                    a.flow_y_max = flow_y_max.data_ptr()
             # the weight images in the workspace are clip-invariant: repacked only when the workspace or the arithmetic changed
             # (the parameters may alias live model tensors -- .to() is a no-op for cuda fp32 -- so their version counters are
             # part of the key: an in-place update by the owner of the weights forces a repack)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_launch_counter(lib):
-    assert lib.motif_abi_version() == 3
+    assert lib.motif_abi_version() == 4
     lib.motif_reset_launch_count()
     assert lib.motif_launch_count() == 0
 
@@ -57,6 +57,7 @@ def test_ctypes_struct_matches_header_layout(lib):
     # 6 ints + 4 pointers + 1 float (+ padding) for the geometry block
     assert ctypes.sizeof(_lib.GeomT) == 6 * 4 + 4 * 8 + 8
     assert ctypes.sizeof(_lib.SirenT) == 8 + 5 * 8 * 2
+    assert ctypes.sizeof(_lib.DecodeT) == lib.motif_sizeof_decode_t()  # the binding's struct is the library's
 
 
 def test_operators_refuse_cpu_tensors():

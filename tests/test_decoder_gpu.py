@@ -364,3 +364,48 @@ def test_clip_stream_matches_resident_decode():
     for c, o in zip(clips, outs):
         ref, _ = dec.decode(c[0].cuda(), c[1].cuda(), c[2].cuda(), tt, (HH, WW), return_flow=False)
         assert (o - ref[1:3].cpu()).abs().max().item() < 1e-5
+
+
+def test_row_bands_assemble_to_the_full_decode():
+    """SURVEY 8e, second sharding axis: destination row bands with a source halo.  Every band decoded on its own (as another
+    rank would) reproduces the rows of the full decode; the reported max |flow_y| is the one of the full flow field; a halo
+    that is too small is detected by the same number."""
+    from motif_b200 import sharding, synthetic
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    B, H, W, HH, WW = 1, 24, 20, 96, 80
+    feat, ff, res = [t.cuda() for t in synthetic.synthetic_latents(B, H, W, seed=4)]
+    params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
+    tt = torch.tensor([[0.2, 0.5, 0.9]])
+    dec = SpaceTimeDecoder(params, device="cuda", precision="f16x3")
+    full, flow = dec.decode(feat, ff, res, tt, (HH, WW))
+    fy_max = (flow[:, 1].abs() * 20.0 * (HH / H)).max().item()
+    halo = int(fy_max) + 3
+    for world in (2, 3, 5):
+        bands = sharding.partition_rows(HH, world)
+        assert bands[0][0] == 0 and bands[-1][1] == HH and all(b % 8 == 0 for b, _ in bands)
+        out = torch.full_like(full, -1.0)
+        seen = 0.0
+        for r0, r1 in bands:
+            if r1 == r0:
+                continue
+            stat = torch.zeros(64, device="cuda")
+            part, pflow = SpaceTimeDecoder(params, device="cuda", precision="f16x3").decode(feat, ff, res, tt, (HH, WW), row_range=(r0, r1), halo=halo, flow_y_max=stat)
+            out[..., r0:r1, :] = part[..., r0:r1, :]
+            s0, s1 = max(r0 - halo, 0), min(r1 + halo, HH)
+            assert torch.equal(pflow[..., s0:s1, :], flow[..., s0:s1, :])      # flows of the evaluated source rows are the same numbers
+            seen = max(seen, sharding.check_halo(stat, halo))
+        assert (out - full).abs().max().item() < 1e-5, world
+        assert abs(seen - fy_max) < 1e-5 and seen < halo - 1
+    # halo too small: the decode of a middle band misses contributions, and the check says so
+    r0, r1 = sharding.partition_rows(HH, 3)[1]
+    stat = torch.zeros(64, device="cuda")
+    tiny = 1
+    dec.decode(feat, ff, res, tt, (HH, WW), row_range=(r0, r1), halo=tiny, flow_y_max=stat)
+    assert sharding.check_halo(stat, tiny) >= tiny - 1
+    again, _ = dec.decode(feat, ff, res, tt, (HH, WW))                          # the workspace is intact after band decodes
+    assert (again - full).abs().max().item() < 1e-5
+    with pytest.raises(Exception):
+        dec.decode(feat, ff, res, tt, (HH, WW), row_range=(4, 40), halo=halo)    # not a multiple of 8
+    with pytest.raises(Exception):
+        dec.decode(feat, ff, res, tt, (HH, WW), row_range=(0, 48), halo=halo, precision="fp32")

@@ -74,6 +74,63 @@ def _worker(rank, world, port, n_ts):
         dist.destroy_process_group()
 
 
+def test_partition_rows_covers_the_frame_in_aligned_bands():
+    from motif_b200 import sharding
+
+    for n_rows, world in ((720, 8), (720, 7), (630, 4), (2160, 8), (20, 4), (8, 3), (5, 2)):
+        bands = sharding.partition_rows(n_rows, world)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == n_rows
+        assert all(b <= e and (b % 8 == 0 or b == e) for b, e in bands)   # empty bands (more ranks than blocks) sit at the end
+        assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+        sizes = [e - b for b, e in bands if e > b]
+        assert max(sizes) - min(sizes) <= 8 + 7          # balanced up to one block (and the ragged last block)
+
+
+def _halo_worker(rank, world, port):
+    import torch.distributed as dist
+
+    from motif_b200 import sharding
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        stat = torch.zeros(64)
+        stat[3] = 5.5 if rank == 0 else 9.25
+        assert sharding.check_halo(stat, 16) == 9.25     # the maximum over the ranks' bands, on every rank
+    finally:
+        dist.destroy_process_group()
+
+
+def _exchange_worker(rank, world, port):
+    import torch.distributed as dist
+
+    from motif_b200 import sharding, synthetic
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        shapes = [(2, 64, 4, 6), (2, 64, 4, 6), (1, 64, 4, 6)]
+        ex = sharding.LatentExchange(shapes, "cpu", src=0)
+        clips = [synthetic.synthetic_latents(1, 4, 6, seed=s) for s in range(3)]
+        ex.start(clips[0] if rank == 0 else None)
+        for k in range(3):
+            got = ex.take()
+            assert all(torch.equal(a, b) for a, b in zip(got, clips[k]))
+            ex.release()
+            if k + 1 < 3:
+                ex.start(clips[k + 1] if rank == 0 else None)
+        with pytest.raises(RuntimeError):
+            ex.take()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_latent_exchange_pipeline():
+    mp.spawn(_exchange_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+def test_two_rank_gloo_halo_check():
+    mp.spawn(_halo_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("n_ts", [7, 1])
 def test_two_rank_gloo_broadcast_and_gather(n_ts):
     mp.spawn(_worker, args=(2, _free_port(), n_ts), nprocs=2, join=True)
