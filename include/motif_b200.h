@@ -176,7 +176,7 @@ typedef struct {
                         * 1 = the four shifted latents blended by diagonally swapped area weights.  Implemented by
                         * MOTIF_PRECISION_FP32 only (other precisions return MOTIF_E_UNSUPPORTED).       */
   /* Destination row band of a sharded decode (MOTIF_PRECISION_F16X3 only).  row_end == 0: the whole image.
-   * Otherwise only the destination rows [row_begin, row_end) of `rgb` are produced (row_begin and row_end multiples of 8, or
+   * Otherwise only the destination rows [row_begin, row_end) of `rgb` are produced (row_begin and row_end multiples of 32, or
    * row_end == HH) and only the sources of rows [row_begin - halo, row_end + halo) are evaluated (`flow_out` is written for
    * those rows only): correct iff no source outside them lands inside the band, i.e. iff max |flow_y| < halo - 1 HR pixels
    * everywhere.  flow_y_max (device, 64 words, may be NULL) receives the float bit patterns whose maximum is the largest

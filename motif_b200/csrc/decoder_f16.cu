@@ -1258,23 +1258,21 @@ constexpr int kBandBlockRows = 4;  // block rows (of kGH destination rows) per L
 // (one LDG.128 per list entry and lane, a half-warp reads one 256-byte source row).  All rows of a destination
 // (first 8 entries, then the rare 9..16) are requested back to back before the first is used; slots past the list
 // length are predicated off, never zero-filled.
-// kBand: only `blocks_y_band` block rows of the image, starting at block blk0, are processed (a destination row band of a sharded
-// decode).  The whole-image instantiation is kept textually identical to the kernel this was tuned as: ptxas's schedule of
-// the body is fragile (the same body behind a slightly different prologue measured 2.57 instead of 2.04 ms).
-template <bool kBand>
+// A destination row band of a sharded decode is a contiguous range of this band-major CTA order (bands are aligned to the L2
+// bands): the launch covers the range and bid0 is its first CTA.
 __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, Scratch sc,
-                                                          float* __restrict__ dbg_pre0, int band_rows, int blk0, int blocks_y_band) {
+                                                          float* __restrict__ dbg_pre0, int band_rows, int bid0) {
   __shared__ uint2 ent_s[kGH][kGW][kSlots];  // the warp's 32 destination lists (4 KB per warp)
   __shared__ float4 par_s[kGH][kGW][2];      // per-destination scalars (1 KB per warp)
   __shared__ float4 rk_s[16][7];             // rank-1 layer-0 weights per 4-channel group (every warp writes the same values)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
   const int qs = g.HH * g.WW, P = g.H * g.W;
-  const int blocks_x = (g.WW + kGW - 1) / kGW, blocks_y = kBand ? blocks_y_band : (g.HH + kGH - 1) / kGH;
+  const int blocks_x = (g.WW + kGW - 1) / kGW, blocks_y = (g.HH + kGH - 1) / kGH;
   int blk, nl;
   {
     const int per_band = band_rows * blocks_x;                  // blocks of one timestamp in a full band
     const int full = (blocks_y / band_rows) * nt * per_band;    // blocks of all full bands
-    int bid = (int)blockIdx.x;
+    int bid = (int)blockIdx.x + bid0;
     if (bid < full) {
       const int band = bid / (nt * per_band), r = bid - band * nt * per_band;
       nl = r / per_band;
@@ -1287,7 +1285,6 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
     }
   }
   const float t = time_of(times, nl);
-  if (kBand) blk += blk0;  // from here on the block's index in the whole image
   const int qy = (blk / blocks_x) * kGH + warp;
   const int x0 = (blk % blocks_x) * kGW;
   if (qy >= g.HH) return;  // whole warps only; no block-wide barrier below
@@ -1350,7 +1347,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
   const float4* Y4 = reinterpret_cast<const float4*>(sc.Y) + l16;
   const float4* R4 = reinterpret_cast<const float4*>(sc.rtab + (size_t)b * P * 64) + l16;
   const int bn = b * N + n0 + nl;
-  uint32_t* a0_out = sc.a0 + (((size_t)nl * B + b) * ((size_t)blocks_x * (kBand ? (g.HH + kGH - 1) / kGH : blocks_y)) * (kGW * kGH) + ((size_t)blk * kGH + warp) * kGW) * 64;
+  uint32_t* a0_out = sc.a0 + (((size_t)nl * B + b) * ((size_t)blocks_x * blocks_y) * (kGW * kGH) + ((size_t)blk * kGH + warp) * kGW) * 64;
 
 #ifndef MOTIF_GATHER_UNROLL
 #define MOTIF_GATHER_UNROLL 2  // two destinations pairs per trip: 2.06 -> 2.03 ms (12 bytes of spills at the 80-register cap)
@@ -1677,10 +1674,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sq));
     const int carve = getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 50;
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
     MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -1704,9 +1698,10 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   Band band;
   band.row_begin = 0, band.row_end = g.HH, band.src_begin = 0, band.src_end = g.HH, band.flow_y_max = nullptr;
   if (a->row_end > 0) {
-    MOTIF_REQUIRE(a->row_begin >= 0 && a->row_begin < a->row_end && a->row_end <= g.HH && a->row_begin % kGH == 0 && (a->row_end % kGH == 0 || a->row_end == g.HH) &&
-                      a->halo >= 0,
-                  "decode: bad destination row band [%d,%d) (multiples of %d inside [0,%d]) or halo %d", a->row_begin, a->row_end, kGH, g.HH, a->halo);
+    constexpr int kAlign = kBandBlockRows * kGH;  // bands are whole L2 bands of the gather kernel's CTA order (32 rows)
+    MOTIF_REQUIRE(a->row_begin >= 0 && a->row_begin < a->row_end && a->row_end <= g.HH && a->row_begin % kAlign == 0 &&
+                      (a->row_end % kAlign == 0 || a->row_end == g.HH) && a->halo >= 0,
+                  "decode: bad destination row band [%d,%d) (multiples of %d inside [0,%d]) or halo %d", a->row_begin, a->row_end, kAlign, g.HH, a->halo);
     band.row_begin = a->row_begin, band.row_end = a->row_end;
     band.src_begin = a->row_begin - a->halo > 0 ? a->row_begin - a->halo : 0;
     band.src_end = a->row_end + a->halo < g.HH ? a->row_end + a->halo : g.HH;
@@ -1739,12 +1734,12 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       }
       {
         ProfScope prof("gather_l0_kernel", st);
-        static const int band_rows = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : kBandBlockRows;
+        static const int band_rows_env = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : kBandBlockRows;
+        const int band_rows = a->row_end > 0 ? kBandBlockRows : band_rows_env;  // tuning hook for the whole-image order only
         static const int dsmem = getenv("MOTIF_GATHER_DSMEM") ? atoi(getenv("MOTIF_GATHER_DSMEM")) : 0;
-        if (a->row_end > 0)
-          gather_l0_kernel<true><<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, by0 * blocks_x, by1 - by0);
-        else
-          gather_l0_kernel<false><<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, 0, 0);
+        // band mode: the band's blocks are the CTAs [bid0, bid0 + nt * band_blocks) of the whole image's band-major order
+        const int bid0 = (by0 / band_rows) * nt * band_rows * blocks_x;
+        gather_l0_kernel<<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, bid0);
         MOTIF_LAUNCHED("gather_l0_kernel");
       }
       {

@@ -177,7 +177,7 @@ class SpaceTimeDecoder:
         or the ``[B*N,64,HH,WW]`` layer-0 pre-activation of synth_net when ``debug_pre0`` -- precision ``f16x3``,
         which never forms the 198-channel input).  ``out``: optional preallocated frame buffer (``ClipStream``).
 
-        ``row_range=(r0, r1)`` (multiples of 8, or ``r1 == HH``) decodes only the destination rows ``[r0, r1)`` of every
+        ``row_range=(r0, r1)`` (multiples of 32, or ``r1 == HH``) decodes only the destination rows ``[r0, r1)`` of every
         frame -- the other rows of ``rgb`` are left untouched -- from the sources of rows ``[r0 - halo, r1 + halo)``
         (the second sharding axis).  Exact iff no source outside them lands in the band, i.e. iff
         ``max |flow_y| < halo - 1`` HR pixels; ``flow_y_max`` (a 64-element fp32 CUDA tensor) receives values whose maximum is
