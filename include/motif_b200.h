@@ -150,6 +150,9 @@ int motif_query_geometry(const motif_geom_t* g, int32_t* iy, int32_t* ix, float*
 
 /* LR latents NCHW -> pixel-major ("channel-last") [rows, H*W, 64]; rows = leading dim. */
 int motif_pack_latents(const float* nchw, float* packed, int rows, int channels, int hw, void* stream);
+/* The same for the pixels [p_begin, p_end) of every plane only (the LR rows a destination row band of a sharded decode reads:
+ * rows [floor(s0 * H / HH) - 1, ceil(s1 * H / HH) + 1) for the source rows [s0, s1) = the band widened by its halo). */
+int motif_pack_latents_range(const float* nchw, float* packed, int rows, int channels, int hw, int p_begin, int p_end, void* stream);
 
 typedef struct {
   motif_geom_t geom;
@@ -176,7 +179,7 @@ typedef struct {
                         * 1 = the four shifted latents blended by diagonally swapped area weights.  Implemented by
                         * MOTIF_PRECISION_FP32 only (other precisions return MOTIF_E_UNSUPPORTED).       */
   /* Destination row band of a sharded decode (MOTIF_PRECISION_F16X3 only).  row_end == 0: the whole image.
-   * Otherwise only the destination rows [row_begin, row_end) of `rgb` are produced (row_begin and row_end multiples of 32, or
+   * Otherwise only the destination rows [row_begin, row_end) of `rgb` are produced (row_begin and row_end multiples of 16, or
    * row_end == HH) and only the sources of rows [row_begin - halo, row_end + halo) are evaluated (`flow_out` is written for
    * those rows only): correct iff no source outside them lands inside the band, i.e. iff max |flow_y| < halo - 1 HR pixels
    * everywhere.  flow_y_max (device, 64 words, may be NULL) receives the float bit patterns whose maximum is the largest

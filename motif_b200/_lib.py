@@ -33,6 +33,7 @@ EXPORTS = [
     "motif_dcn_v2_fwd",
     "motif_query_geometry",
     "motif_pack_latents",
+    "motif_pack_latents_range",
     "motif_decode_workspace_bytes",
     "motif_sizeof_decode_t",
     "motif_decode",
@@ -119,6 +120,8 @@ def _declare(lib):
     lib.motif_query_geometry.argtypes = [POINTER(GeomT), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.motif_pack_latents.restype = c_int
     lib.motif_pack_latents.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
+    lib.motif_pack_latents_range.restype = c_int
+    lib.motif_pack_latents_range.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_decode_workspace_bytes.restype = c_size_t
     lib.motif_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
     lib.motif_sizeof_decode_t.restype = c_size_t

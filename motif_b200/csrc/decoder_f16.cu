@@ -260,14 +260,14 @@ struct LrJobs {
 };
 // Two LR pixels per thread: every (broadcast) shared-memory load of a weight quad feeds eight FMAs instead of four -- the
 // kernel is bound by the LSU data pipe (a broadcast LDS.128 still writes 512 B back to the register file), not by FP32.
-__global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float* __restrict__ wp, int P) {
+__global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float* __restrict__ wp, int p_begin, int P) {
   __shared__ float4 w4[64 * 16];
   __shared__ float bias[64];
   const LrJob jb = jobs.j[blockIdx.y];
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) w4[i] = *reinterpret_cast<const float4*>(wp + jb.w_off + 4 * i);
   if (threadIdx.x < 64) bias[threadIdx.x] = jb.bias_off >= 0 ? wp[jb.bias_off + threadIdx.x * jb.bias_ld] : 0.0f;
   __syncthreads();
-  const int p0 = blockIdx.x * (2 * blockDim.x) + threadIdx.x, p1 = p0 + blockDim.x;
+  const int p0 = p_begin + blockIdx.x * (2 * blockDim.x) + threadIdx.x, p1 = p0 + blockDim.x;  // LR pixels [p_begin, P)
   if (p0 >= P) return;
   const bool two = p1 < P;
   float x0[64], x1[64];
@@ -1250,6 +1250,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 constexpr int kBandBlockRows = 4;  // block rows (of kGH destination rows) per L2 band
+constexpr int kBandBlockRowsSharded = 2;  // ... of a destination-row-band decode (2 measured 2.05 vs 2.04 ms; finer bands balance better)
 
 // Grid = (timestamps of the group) x (32 x 8 destination blocks), ordered BAND-major: all timestamps of a band of
 // kBandBlockRows block rows run back to back, so the per-source rows Y they share (both reference frames, ~21 MB per
@@ -1572,10 +1573,11 @@ static int prepare_weights(const motif_decode_t* a, const Scratch& sc, cudaStrea
   return 0;
 }
 
-static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) {
+static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st, int lr_row_begin, int lr_row_end) {
   using Wp = WeightPack;
   const motif_geom_t& g = a->geom;
   const int P = g.H * g.W, B = g.B;
+  const int p_begin = lr_row_begin * g.W, p_end = lr_row_end * g.W;  // LR pixels the decoded band can select
   if (!a->weights_ready)
     if (int rc = prepare_weights(a, sc, st)) return rc;
 #ifndef MOTIF_OUT3_SMEM
@@ -1600,7 +1602,7 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
     lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.p0i + (size_t)rb * P * 64, Wp::i_a0, -1, 0};
     lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.ftab + (size_t)rb * P * 64, Wp::s_a0b, -1, 0};
     if (nj + 4 > 16) {
-      lr_tables_kernel<<<dim3(ceil_div(P, 256), nj), 128, 0, st>>>(lj, sc.wpack, P);
+      lr_tables_kernel<<<dim3(ceil_div(p_end - p_begin, 256), nj), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end);
       MOTIF_LAUNCHED("lr_tables_kernel");
       nj = 0;
     }
@@ -1608,13 +1610,13 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st) 
   for (int b = 0; b < B; ++b) {
     lj.j[nj++] = LrJob{a->residual + (size_t)b * P * 64, sc.rtab + (size_t)b * P * 64, Wp::s_a0c, Wp::s_e0, 8};
     if (nj == 16) {
-      lr_tables_kernel<<<dim3(ceil_div(P, 256), nj), 128, 0, st>>>(lj, sc.wpack, P);
+      lr_tables_kernel<<<dim3(ceil_div(p_end - p_begin, 256), nj), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end);
       MOTIF_LAUNCHED("lr_tables_kernel");
       nj = 0;
     }
   }
   if (nj > 0) {
-    lr_tables_kernel<<<dim3(ceil_div(P, 256), nj), 128, 0, st>>>(lj, sc.wpack, P);
+    lr_tables_kernel<<<dim3(ceil_div(p_end - p_begin, 256), nj), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end);
     MOTIF_LAUNCHED("lr_tables_kernel");
   }
   return 0;
@@ -1693,12 +1695,11 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   MOTIF_LAUNCHED("arm_kernel");
   mark_kernel<<<1, 32, 0, st>>>(sc.armed, none);
   MOTIF_LAUNCHED("mark_kernel");
-  if (int rc = prepare(a, sc, st)) return rc;
   // destination row band of a sharded decode (the whole image when row_end == 0): sources of the band widened by the halo
   Band band;
   band.row_begin = 0, band.row_end = g.HH, band.src_begin = 0, band.src_end = g.HH, band.flow_y_max = nullptr;
   if (a->row_end > 0) {
-    constexpr int kAlign = kBandBlockRows * kGH;  // bands are whole L2 bands of the gather kernel's CTA order (32 rows)
+    constexpr int kAlign = kBandBlockRowsSharded * kGH;  // bands are whole L2 bands of the gather kernel's CTA order (16 rows)
     MOTIF_REQUIRE(a->row_begin >= 0 && a->row_begin < a->row_end && a->row_end <= g.HH && a->row_begin % kAlign == 0 &&
                       (a->row_end % kAlign == 0 || a->row_end == g.HH) && a->halo >= 0,
                   "decode: bad destination row band [%d,%d) (multiples of %d inside [0,%d]) or halo %d", a->row_begin, a->row_end, kAlign, g.HH, a->halo);
@@ -1707,6 +1708,12 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     band.src_end = a->row_end + a->halo < g.HH ? a->row_end + a->halo : g.HH;
     band.flow_y_max = reinterpret_cast<unsigned int*>(a->flow_y_max);
     if (band.flow_y_max != nullptr) MOTIF_CUDA(cudaMemsetAsync(band.flow_y_max, 0, 64 * sizeof(unsigned int), st));
+  }
+  {
+    // LR rows whose latents the band's source rows can select (nearest latent, one row of slack; SpaceTimeDecoder.lr_rows_of_band)
+    const int lr0 = (int)(((long long)band.src_begin * g.H) / g.HH) - 1, lr1 = (int)(((long long)band.src_end * g.H + g.HH - 1) / g.HH) + 1;
+    const bool whole = a->row_end <= 0;
+    if (int rc = prepare(a, sc, st, whole || lr0 < 0 ? 0 : lr0, whole || lr1 > g.H ? g.H : lr1)) return rc;
   }
   const int q_begin = band.src_begin * g.WW, q_end = band.src_end * g.WW;
   const int tiles128 = ceil_div((long long)(q_end - q_begin), 128);  // 128-pixel runs of source pixels
@@ -1735,7 +1742,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       {
         ProfScope prof("gather_l0_kernel", st);
         static const int band_rows_env = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : kBandBlockRows;
-        const int band_rows = a->row_end > 0 ? kBandBlockRows : band_rows_env;  // tuning hook for the whole-image order only
+        const int band_rows = a->row_end > 0 ? kBandBlockRowsSharded : band_rows_env;  // tuning hook for the whole-image order only
         static const int dsmem = getenv("MOTIF_GATHER_DSMEM") ? atoi(getenv("MOTIF_GATHER_DSMEM")) : 0;
         // band mode: the band's blocks are the CTAs [bid0, bid0 + nt * band_blocks) of the whole image's band-major order
         const int bid0 = (by0 / band_rows) * nt * band_rows * blocks_x;

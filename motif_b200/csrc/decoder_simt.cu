@@ -422,20 +422,21 @@ __global__ void geometry_kernel(motif_geom_t g, int32_t* iy, int32_t* ix, float*
 }
 
 // NCHW [rows][C][hw] -> [rows][hw][C] through a 32x32 shared tile
-__global__ void pack_latents_kernel(const float* __restrict__ in, float* __restrict__ out, int c, int hw) {
+// pixels [p_begin, p_end) of every plane (the LR rows a destination row band needs; everything by default)
+__global__ void pack_latents_kernel(const float* __restrict__ in, float* __restrict__ out, int c, int hw, int p_begin, int p_end) {
   __shared__ float tile[32][33];
   const int row = blockIdx.z;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int p0 = p_begin + blockIdx.x * 32, c0 = blockIdx.y * 32;
   const float* src = in + (size_t)row * c * hw;
   float* dst = out + (size_t)row * c * hw;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int ch = c0 + i, p = p0 + threadIdx.x;
-    tile[i][threadIdx.x] = (ch < c && p < hw) ? src[(size_t)ch * hw + p] : 0.0f;
+    tile[i][threadIdx.x] = (ch < c && p < p_end) ? src[(size_t)ch * hw + p] : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, ch = c0 + threadIdx.x;
-    if (p < hw && ch < c) dst[(size_t)p * c + ch] = tile[threadIdx.x][i];
+    if (p < p_end && ch < c) dst[(size_t)p * c + ch] = tile[threadIdx.x][i];
   }
 }
 
@@ -618,7 +619,17 @@ extern "C" int motif_pack_latents(const float* nchw, float* packed, int rows, in
   MOTIF_REQUIRE(nchw && packed, "pack_latents: null pointer");
   MOTIF_REQUIRE(rows > 0 && channels > 0 && hw > 0 && rows <= 65535, "pack_latents: bad size");
   dim3 grid(ceil_div(hw, 32), ceil_div(channels, 32), rows);
-  pack_latents_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(nchw, packed, channels, hw);
+  pack_latents_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(nchw, packed, channels, hw, 0, hw);
+  MOTIF_LAUNCHED("pack_latents_kernel");
+  return 0;
+}
+
+extern "C" int motif_pack_latents_range(const float* nchw, float* packed, int rows, int channels, int hw, int p_begin, int p_end, void* stream) {
+  MOTIF_REQUIRE(nchw && packed, "pack_latents: null pointer");
+  MOTIF_REQUIRE(rows > 0 && channels > 0 && hw > 0 && rows <= 65535 && p_begin >= 0 && p_begin <= p_end && p_end <= hw, "pack_latents: bad size or range");
+  if (p_begin == p_end) return 0;
+  dim3 grid(ceil_div(p_end - p_begin, 32), ceil_div(channels, 32), rows);
+  pack_latents_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(nchw, packed, channels, hw, p_begin, p_end);
   MOTIF_LAUNCHED("pack_latents_kernel");
   return 0;
 }

@@ -143,17 +143,28 @@ class SpaceTimeDecoder:
         _lib.check(rc, "motif_query_geometry")
         return iy, ix, coord, rel
 
-    def pack_latents(self, x: torch.Tensor) -> torch.Tensor:
-        """NCHW ``[R, C, H, W]`` -> pixel-major ``[R, H*W, C]`` (device transpose kernel)."""
+    def pack_latents(self, x: torch.Tensor, lr_rows: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """NCHW ``[R, C, H, W]`` -> pixel-major ``[R, H*W, C]`` (device transpose kernel).  ``lr_rows``: only these LR rows are
+        transposed (a destination row band never reads the others; the rest of the result is uninitialised)."""
         lib = _lib.load()
         _lib.require_cuda_f32("latents", x, 4)
         x = x.contiguous()
         r, c, h, w = x.shape
         out = torch.empty(r, h * w, c, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            rc = lib.motif_pack_latents(x.data_ptr(), out.data_ptr(), r, c, h * w, _lib.current_stream_ptr(x.device))
+            if lr_rows is None:
+                rc = lib.motif_pack_latents(x.data_ptr(), out.data_ptr(), r, c, h * w, _lib.current_stream_ptr(x.device))
+            else:
+                rc = lib.motif_pack_latents_range(x.data_ptr(), out.data_ptr(), r, c, h * w, lr_rows[0] * w, lr_rows[1] * w, _lib.current_stream_ptr(x.device))
         _lib.check(rc, "motif_pack_latents")
         return out
+
+    @staticmethod
+    def lr_rows_of_band(H: int, HH: int, row_range: Tuple[int, int], halo: int) -> Tuple[int, int]:
+        """LR rows whose latents the HR source rows ``[r0 - halo, r1 + halo)`` can select (nearest latent, one row of slack):
+        the same bound the library uses for its per-LR-pixel tables."""
+        s0, s1 = max(row_range[0] - halo, 0), min(row_range[1] + halo, HH)
+        return max((s0 * H) // HH - 1, 0), min(-((-s1 * H) // HH) + 1, H)
 
     def decode(
         self,
@@ -177,7 +188,7 @@ class SpaceTimeDecoder:
         or the ``[B*N,64,HH,WW]`` layer-0 pre-activation of synth_net when ``debug_pre0`` -- precision ``f16x3``,
         which never forms the 198-channel input).  ``out``: optional preallocated frame buffer (``ClipStream``).
 
-        ``row_range=(r0, r1)`` (multiples of 32, or ``r1 == HH``) decodes only the destination rows ``[r0, r1)`` of every
+        ``row_range=(r0, r1)`` (multiples of 16, or ``r1 == HH``) decodes only the destination rows ``[r0, r1)`` of every
         frame -- the other rows of ``rgb`` are left untouched -- from the sources of rows ``[r0 - halo, r1 + halo)``
         (the second sharding axis).  Exact iff no source outside them lands in the band, i.e. iff
         ``max |flow_y| < halo - 1`` HR pixels; ``flow_y_max`` (a 64-element fp32 CUDA tensor) receives values whose maximum is
@@ -196,9 +207,10 @@ class SpaceTimeDecoder:
         n0, n1 = (0, N) if n_range is None else n_range
         dev = self.device
         with torch.cuda.device(dev):
-            featp = self.pack_latents(feat)
-            ffp = self.pack_latents(flow_feat)
-            resp = self.pack_latents(residual)
+            lr_rows = None if row_range is None else self.lr_rows_of_band(H, HH, row_range, halo)
+            featp = self.pack_latents(feat, lr_rows)
+            ffp = self.pack_latents(flow_feat, lr_rows)
+            resp = self.pack_latents(residual, lr_rows)
             if out is not None:
                 if out.shape != (N, B, 3, HH, WW) or out.dtype != torch.float32 or out.device != residual.device or not out.is_contiguous():
                     raise ValueError(f"out must be a contiguous fp32 [{N},{B},3,{HH},{WW}] tensor on {dev}")

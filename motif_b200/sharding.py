@@ -25,9 +25,9 @@ def partition_timestamps(n_timestamps: int, world_size: int) -> List[Tuple[int, 
     return out
 
 
-def partition_rows(n_rows: int, world_size: int, align: int = 32) -> List[Tuple[int, int]]:
+def partition_rows(n_rows: int, world_size: int, align: int = 16) -> List[Tuple[int, int]]:
     """Contiguous destination row bands ``[begin, end)``, one per rank, begins aligned to ``align`` rows (the L2 band of the
-    gather kernel's CTA order: four 8-row blocks), as balanced as the alignment allows (a band may be empty when there are more ranks than blocks)."""
+    gather kernel's CTA order in band mode: two 8-row blocks), as balanced as the alignment allows (a band may be empty when there are more ranks than blocks)."""
     blocks = (n_rows + align - 1) // align
     base, extra = divmod(blocks, world_size)
     out, start = [], 0

@@ -373,7 +373,7 @@ def test_row_bands_assemble_to_the_full_decode():
     from motif_b200 import sharding, synthetic
     from motif_b200.decoder import SpaceTimeDecoder
 
-    B, H, W, HH, WW = 1, 44, 20, 176, 80      # 5.5 aligned bands of 32 rows
+    B, H, W, HH, WW = 1, 22, 20, 88, 80       # 5.5 aligned bands of 16 rows
     feat, ff, res = [t.cuda() for t in synthetic.synthetic_latents(B, H, W, seed=4)]
     params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
     tt = torch.tensor([[0.2, 0.5, 0.9]])
@@ -383,7 +383,7 @@ def test_row_bands_assemble_to_the_full_decode():
     halo = int(fy_max) + 3
     for world in (2, 3, 5):
         bands = sharding.partition_rows(HH, world)
-        assert bands[0][0] == 0 and bands[-1][1] == HH and all(b % 32 == 0 or b == e for b, e in bands)
+        assert bands[0][0] == 0 and bands[-1][1] == HH and all(b % 16 == 0 or b == e for b, e in bands)
         out = torch.full_like(full, -1.0)
         seen = 0.0
         for r0, r1 in bands:
@@ -406,6 +406,6 @@ def test_row_bands_assemble_to_the_full_decode():
     again, _ = dec.decode(feat, ff, res, tt, (HH, WW))                          # the workspace is intact after band decodes
     assert (again - full).abs().max().item() < 1e-5
     with pytest.raises(Exception):
-        dec.decode(feat, ff, res, tt, (HH, WW), row_range=(8, 64), halo=halo)    # not a multiple of 32
+        dec.decode(feat, ff, res, tt, (HH, WW), row_range=(8, 64), halo=halo)    # not a multiple of 16
     with pytest.raises(Exception):
         dec.decode(feat, ff, res, tt, (HH, WW), row_range=(0, 64), halo=halo, precision="fp32")

@@ -80,10 +80,10 @@ def test_partition_rows_covers_the_frame_in_aligned_bands():
     for n_rows, world in ((720, 8), (720, 7), (630, 4), (2160, 8), (20, 4), (8, 3), (5, 2)):
         bands = sharding.partition_rows(n_rows, world)
         assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == n_rows
-        assert all(b <= e and (b % 32 == 0 or b == e) for b, e in bands)   # empty bands (more ranks than blocks) sit at the end
+        assert all(b <= e and (b % 16 == 0 or b == e) for b, e in bands)   # empty bands (more ranks than blocks) sit at the end
         assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
         sizes = [e - b for b, e in bands if e > b]
-        assert max(sizes) - min(sizes) <= 32 + 31        # balanced up to one aligned band (and the ragged last one)
+        assert max(sizes) - min(sizes) <= 16 + 15        # balanced up to one aligned band (and the ragged last one)
 
 
 def _halo_worker(rank, world, port):
