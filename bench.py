@@ -145,11 +145,18 @@ def main():
     ap.add_argument("--workload", default="adobe240_x4_t8")
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "tf32x3", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="bands", choices=["bands", "clips"],
+                    help="N > 1: 'bands' = ONE clip sharded by destination row bands (BASELINE config 3, strong scaling); "
+                         "'clips' = one clip per GPU, no collective (BASELINE config 5: --workload uhd4k_x4_t8, weak scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_ranks = world                      # processes of the job
+    per_clip = args.parallel == "clips" and world > 1
+    if per_clip:
+        world = 1                        # from here on `world` = ranks that share ONE clip; every rank decodes its own clip alone
 
     from motif_b200 import synthetic
 
@@ -159,7 +166,7 @@ def main():
     HALO = 16  # source halo (HR rows) of a destination row band; checked against the largest |flow_y| after the timed loops
     config = {"workload": f"{args.workload}: LR {H}x{W} -> HR {HH}x{WW}, {N} timestamps, B=1, synthetic latents + synthetic best.pth-layout weights",
               "l2": "per-step working set (per-source rows 472 MB + destination lists 118 MB + frames 77 MB) >> 126 MB L2; no explicit flush",
-              "parallelism": (f"destination row bands (+{HALO}-row source halo, verified) over {world} ranks, every rank all {N} timestamps; NCCL broadcast of the "
+              "parallelism": f"one clip per GPU on {n_ranks} GPUs, no collective (data parallel by clip)" if per_clip else (f"destination row bands (+{HALO}-row source halo, verified) over {world} ranks, every rank all {N} timestamps; NCCL broadcast of the "
                               "LR latents per step on a side stream, overlapped with the previous step's decode") if world > 1 else "single GPU"}
 
     if args.impl == "reference":
@@ -191,14 +198,14 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if n_ranks > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
     params = synthetic.synthetic_params(seed=0)
     dec = SpaceTimeDecoder(params, device=dev, precision=args.precision)
-    feat_h, ff_h, res_h = [t.pin_memory() for t in synthetic.synthetic_latents(B, H, W, seed=0)]
-    if rank == 0:
+    feat_h, ff_h, res_h = [t.pin_memory() for t in synthetic.synthetic_latents(B, H, W, seed=rank if per_clip else 0)]
+    if rank == 0 or per_clip:
         feat, ff, res = feat_h.to(dev), ff_h.to(dev), res_h.to(dev)
     else:
         feat, ff, res = [torch.empty_like(t, device=dev) for t in (feat_h, ff_h, res_h)]
@@ -223,7 +230,7 @@ def main():
         public host-buffer API -- pinned latents copied in, frames copied out, double-buffered against the
         neighbouring clips' decode (motif_b200/clip_stream.py); every clip's copies happen inside the timed region."""
         if from_host:
-            if rank == 0:
+            if rank == 0 or per_clip:
                 stream.submit(feat_h, ff_h, res_h, tt, (HH, WW), out_h, n_range=(n0, n1), **band)
             else:
                 stream.submit(None, None, None, tt, (HH, WW), out_h, n_range=(n0, n1), shapes=lat_shapes, **band)
@@ -239,8 +246,9 @@ def main():
             exchange.release()
 
     def timed(from_host: bool, steps: int, profile: bool):
-        if world > 1:
+        if n_ranks > 1:
             dist.barrier()
+        if world > 1:
             if not from_host:
                 exchange.start((feat, ff, res) if rank == 0 else None)   # prime the pipeline: the timed region does `steps` broadcasts
         torch.cuda.synchronize()
@@ -261,7 +269,7 @@ def main():
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         launches = lib.motif_launch_count()
-        if world > 1:
+        if n_ranks > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
@@ -300,16 +308,17 @@ def main():
         assert max(fy_resident, fy_host) < HALO - 1, f"source halo of {HALO} rows violated: max |flow_y| = {max(fy_resident, fy_host)}"
         halo_check = {"halo_rows": HALO, "max_abs_flow_y_px": max(fy_resident, fy_host)}
     if rank != 0:
-        if world > 1:
+        if n_ranks > 1:
             dist.destroy_process_group()
         return
 
     peaks = load_peaks()
+    clips = n_ranks if per_clip else 1
     units_per_step = N * qs
-    value = units_per_step * args.steps / (ms * 1e-3)
-    e2e_value = units_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = (feat_h.numel() + ff_h.numel() + res_h.numel()) * 4
-    d2h = N * B * 3 * qs * 4  # all ranks together (each copies its own rows out)
+    value = clips * units_per_step * args.steps / (ms * 1e-3)
+    e2e_value = clips * units_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = clips * (feat_h.numel() + ff_h.numel() + res_h.numel()) * 4
+    d2h = clips * N * B * 3 * qs * 4  # all ranks together (each copies its own rows / clip out)
 
     # ---- roofline of the dominant kernel of the step (per launch, CUDA events on the launch stream) ----
     # Algorithmic work per launch.  Tensor-bound kernels: dense MACs of the reference's layers
@@ -395,13 +404,13 @@ def main():
     del x, fl, z
 
     cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
+    if n_ranks == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(CPU_SAMPLE, 2, 1, CPU_SAMPLE_NOTE)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_ranks, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if per_clip else "strong", "vs_baseline": None,
         "dtype": {"f16x3": "f16x3 (two-piece fp16 split, fp32 accumulate; fp32-equivalent)", "tf32x3": "tf32x3 (fp32-equivalent)", "fp32": "f32"}[args.precision],
         "data": "synthetic", "config": config,
         "clocks": clocks,
@@ -412,7 +421,7 @@ def main():
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
-    if world > 1:
+    if n_ranks > 1:
         dist.destroy_process_group()
 
 

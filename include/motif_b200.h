@@ -117,6 +117,15 @@ int motif_dcn_v2_fwd(const float* in, const float* offset, const float* mask, co
                      int B, int Cin, int Cout, int H, int W, int deformable_groups, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Output path of the evaluation loop.  Replaces the eager crop + L1 + luma + MSE of test.py:187-235.
+ *   fake [n_frames, 3, hp, wp] decoded frames (possibly padded), cropped to the top-left h x w
+ *   real [n_frames, 3, h, w]   ground truth
+ *   out  [n_frames, 2] DOUBLE: sum over RGB of |real - fake|, sum over pixels of (Y(real) - Y(fake))^2 with
+ *        Y = ((255 R * 65.481 + 255 G * 128.553 + 255 B * 24.966) / 255 + 16) / 255 in fp32 as test.py:212-217 forms it
+ * ---------------------------------------------------------------------------------- */
+int motif_frame_metrics(const float* fake, const float* real, double* out, int n_frames, int hp, int wp, int h, int w, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Space-time local implicit decoder.  Replaces models/modules/Ours.py:659-858 (LunaTokis.forward
  * from make_coord to the clamp) with SIREN MLPs of models/modules/SIREN.py:44-45, 76-79.
  * ---------------------------------------------------------------------------------- */

@@ -31,6 +31,7 @@ EXPORTS = [
     "motif_flow_front",
     "motif_raft_corr_lookup",
     "motif_dcn_v2_fwd",
+    "motif_frame_metrics",
     "motif_query_geometry",
     "motif_pack_latents",
     "motif_pack_latents_range",
@@ -116,6 +117,8 @@ def _declare(lib):
     lib.motif_raft_corr_lookup.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_dcn_v2_fwd.restype = c_int
     lib.motif_dcn_v2_fwd.argtypes = [c_void_p] * 6 + [c_int] * 6 + [c_void_p]
+    lib.motif_frame_metrics.restype = c_int
+    lib.motif_frame_metrics.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_query_geometry.restype = c_int
     lib.motif_query_geometry.argtypes = [POINTER(GeomT), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.motif_pack_latents.restype = c_int

@@ -139,3 +139,18 @@ def test_oracle_against_host_compiled_reference_kernels():
     f1 = torch.randn(1, 20, 7, 9, generator=gen)
     f2 = torch.randn(1, 20, 7, 9, generator=gen)
     assert (build_ref.ref_correlation(f1, f2) - correlation_ref.function_correlation(f1, f2)).abs().max().item() < 1e-6
+
+
+def test_metrics_oracle_against_float64():
+    """test.py:187-235 (crop, L1, BT.601 luma, per-frame MSE): the restatement against an independent float64 evaluation."""
+    from oracle import metrics_ref
+
+    g = torch.Generator().manual_seed(3)
+    fake = torch.rand(3, 1, 3, 12, 14, generator=g)
+    real = torch.rand(3, 3, 10, 11, generator=g)
+    loss, mse = metrics_ref.frame_metrics(fake, real)
+    f = fake[:, :, :, :10, :11].reshape(3, 3, 10, 11).double()
+    r = real.double()
+    assert abs(loss - (r - f).abs().mean().item()) < 1e-6
+    y = lambda t: ((t[:, 0] * 255 * 65.481 + t[:, 1] * 255 * 128.553 + t[:, 2] * 255 * 24.966) / 255 + 16) / 255
+    assert torch.allclose(mse.double(), ((y(r) - y(f)) ** 2).flatten(1).mean(1), rtol=1e-4)
