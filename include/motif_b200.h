@@ -186,7 +186,7 @@ typedef struct {
   int precision;       /* MOTIF_PRECISION_*: arithmetic of the three SIREN MLPs               */
   int local_ensemble;  /* LunaTokis.local_ensemble (Ours.py:453, 660-663, 754-764): 0 as shipped = one nearest latent;
                         * 1 = the four shifted latents blended by diagonally swapped area weights.  Implemented by
-                        * MOTIF_PRECISION_FP32 only (other precisions return MOTIF_E_UNSUPPORTED).       */
+                        * MOTIF_PRECISION_F16X3 and MOTIF_PRECISION_FP32 (TF32X3 returns MOTIF_E_UNSUPPORTED). */
   /* Destination row band of a sharded decode (MOTIF_PRECISION_F16X3 only).  row_end == 0: the whole image.
    * Otherwise only the destination rows [row_begin, row_end) of `rgb` are produced (row_begin and row_end multiples of 16, or
    * row_end == HH) and only the sources of rows [row_begin - halo, row_end + halo) are evaluated (`flow_out` is written for

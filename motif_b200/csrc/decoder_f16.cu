@@ -683,7 +683,11 @@ using SmemI = Smem<9, 0>;
 
 // consts: [0,256) e0 float4 (30 b0, 30 w_rely, 30 w_relx, 0)  [256,320) 30 b1  [320,576) 30 b2  [576,640) 30 * folded bias
 //         [640] s1  [641] s2  [642] s3
-__global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, int B, int b, Scratch sc, int q_begin, int q_end) {
+// kEns (LunaTokis.local_ensemble, Ours.py:660-663, 754-764): launched once per shifted latent ens_k = 0..3; the pass evaluates imnet at
+// that latent and ACCUMULATES area-weight * (its row) into Y -- the blend of the four predictions commutes with the linear layers
+// folded into Y (pass 0 overwrites).
+template <bool kEns>
+__global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, int B, int b, Scratch sc, int q_begin, int q_end, int ens_k) {
   extern __shared__ unsigned char smem_raw[];
   SmemI& sm = *reinterpret_cast<SmemI*>(align1024(smem_raw));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -717,7 +721,13 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
       const int q = q_begin + tile_id * 128 + c.quad * 32 + lane;
       const bool live = q < q_end;
       const int qc = live ? q : q_end - 1;
-      const Query qu = make_query(qc / g.WW, qc % g.WW, g);
+      const Query qu = kEns ? ensemble_query(qc / g.WW, qc % g.WW, g, ens_k) : make_query(qc / g.WW, qc % g.WW, g);
+      float wk = 1.0f;
+      if (kEns) {
+        float ew[4];
+        ensemble_weights(qc / g.WW, qc % g.WW, g, ew);
+        wk = pick4(ew, ens_k);
+      }
       const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
       table_layer0(c, sc.p0i + lr * 64, e0, qu.rel_y, qu.rel_x);
       sine_epilogue(c, 0, s1, sm.consts + 256, kColA, &sm.bars.a_ready[c.tile], false);
@@ -737,8 +747,13 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 f = __ldg(f4 + j4);
             const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 576 + 32 * c.half + 4 * j4);
-            dst[j4] = make_float4(fmaf(__uint_as_float(r[4 * j4 + 0]), s3, bb.x) + f.x, fmaf(__uint_as_float(r[4 * j4 + 1]), s3, bb.y) + f.y,
-                                  fmaf(__uint_as_float(r[4 * j4 + 2]), s3, bb.z) + f.z, fmaf(__uint_as_float(r[4 * j4 + 3]), s3, bb.w) + f.w);
+            float4 v = make_float4(fmaf(__uint_as_float(r[4 * j4 + 0]), s3, bb.x) + f.x, fmaf(__uint_as_float(r[4 * j4 + 1]), s3, bb.y) + f.y,
+                                   fmaf(__uint_as_float(r[4 * j4 + 2]), s3, bb.z) + f.z, fmaf(__uint_as_float(r[4 * j4 + 3]), s3, bb.w) + f.w);
+            if (kEns) {
+              const float4 o = ens_k > 0 ? dst[j4] : make_float4(0.f, 0.f, 0.f, 0.f);
+              v = make_float4(fmaf(v.x, wk, o.x), fmaf(v.y, wk, o.y), fmaf(v.z, wk, o.z), fmaf(v.w, wk, o.w));
+            }
+            dst[j4] = v;
           }
         }
       }
@@ -1121,6 +1136,9 @@ __device__ __noinline__ void scatter_item(const ScatterCtx& cx, int item, int ro
 // consts: [0,256) unused  [256,320) 30 b1  [320,1344) output weights per pair of hidden units (see q_sine_out3)  [1344,1347) b3
 //         [1348] s1 [1349] s2   [2048 + 256 nl, +256) e0 of timestamp nl, per pair of units (see q_table_layer0)
 // Work item = (timestamp of the group, reference frame, 128-pixel tile), timestamp-major.
+// kEns: every query is evaluated at the four shifted latents and the three outputs are blended with the area weights BEFORE the flow / z
+// scaling and the splat (Ours.py:758-764, 794); the MMA program simply runs once per latent.
+template <bool kEns>
 __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, float alpha, Scratch sc,
                                                                 float* __restrict__ flow_out, Band band) {
   extern __shared__ unsigned char smem_raw[];
@@ -1196,19 +1214,43 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
       const int q = q_begin + (rem >> 1) * 128 + row;
       const int qc = q < q_end ? q : q_end - 1;
       const int qy = qc / g.WW, qx = qc % g.WW;
-      const Query qu = make_query(qy, qx, g);
-      const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
-      q_table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
-      if (p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
-      TRACE_Q(c, 4);
-      q_sine_epilogue(c, s1, sm.consts + 256);
-      float dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
+      float dx, dy, zraw;
+      if (!kEns) {
+        const Query qu = make_query(qy, qx, g);
+        const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
+        q_table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
+        if (p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
+        TRACE_Q(c, 4);
+        q_sine_epilogue(c, s1, sm.consts + 256);
+        dx = sm.consts[1344], dy = sm.consts[1345], zraw = sm.consts[1346];
 #pragma unroll 1
 #ifndef MOTIF_OUT3_SMEM
-      for (int ch = 0; ch < 4; ++ch) q_sine_out3_c<0>(c, s2, ch, ch < 3, dx, dy, zraw);
+        for (int ch = 0; ch < 4; ++ch) q_sine_out3_c<0>(c, s2, ch, ch < 3, dx, dy, zraw);
 #else
-      for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
+        for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, dx, dy, zraw);
 #endif
+      } else {
+        float ew[4];
+        ensemble_weights(qy, qx, g, ew);
+        dx = dy = zraw = 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const Query qu = ensemble_query(qy, qx, g, k);
+          const size_t lr = (size_t)rb * P + (size_t)qu.iy * g.W + qu.ix;
+          q_table_layer0(c, sc.p0f + lr * 64, e0, qu.rel_y, qu.rel_x);
+          if (k == 0 && p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
+          q_sine_epilogue(c, s1, sm.consts + 256);
+          float ox = sm.consts[1344], oy = sm.consts[1345], oz = sm.consts[1346];
+#pragma unroll 1
+#ifndef MOTIF_OUT3_SMEM
+          for (int ch = 0; ch < 4; ++ch) q_sine_out3_c<0>(c, s2, ch, ch < 3, ox, oy, oz);
+#else
+          for (int ch = 0; ch < 4; ++ch) q_sine_out3(c, s2, cw + 64 * ch, ch < 3, ox, oy, oz);
+#endif
+          const float wk = pick4(ew, k);
+          dx = fmaf(ox, wk, dx), dy = fmaf(oy, wk, dy), zraw = fmaf(oz, wk, zraw);
+        }
+      }
       TRACE_Q(c, 2);
       if (band.flow_y_max != nullptr) {  // halo check of a sharded decode: largest |flow_y| over the sources of the band's own rows
         const bool own = (q < q_end) & (qy >= band.row_begin) & (qy < band.row_end);
@@ -1261,8 +1303,27 @@ constexpr int kBandBlockRowsSharded = 2;  // ... of a destination-row-band decod
 // length are predicated off, never zero-filled.
 // A destination row band of a sharded decode is a contiguous range of this band-major CTA order (bands are aligned to the L2
 // bands): the launch covers the range and bid0 is its first CTA.
+// kEns: the residual term is the area-weighted blend of the four shifted latents' table rows (q_residual, Ours.py:762); the four
+// latent indices (int bits) and weights of every destination of the CTA sit in 8 KB of dynamic shared memory.
+__device__ __forceinline__ float4 (*ens_table())[kGW][2] {
+  extern __shared__ float4 ens_dyn[];
+  return reinterpret_cast<float4(*)[kGW][2]>(ens_dyn);
+}
+__device__ __forceinline__ float4 ens_rr(const float4* __restrict__ R4, int warp, int j) {
+  const float4 ei = ens_table()[warp][j][0], ew = ens_table()[warp][j][1];
+  const float4 r0 = __ldg(R4 + (size_t)__float_as_int(ei.x) * 16), r1 = __ldg(R4 + (size_t)__float_as_int(ei.y) * 16);
+  const float4 r2 = __ldg(R4 + (size_t)__float_as_int(ei.z) * 16), r3 = __ldg(R4 + (size_t)__float_as_int(ei.w) * 16);
+  float4 rr;
+  rr.x = fmaf(r3.x, ew.w, fmaf(r2.x, ew.z, fmaf(r1.x, ew.y, r0.x * ew.x)));
+  rr.y = fmaf(r3.y, ew.w, fmaf(r2.y, ew.z, fmaf(r1.y, ew.y, r0.y * ew.x)));
+  rr.z = fmaf(r3.z, ew.w, fmaf(r2.z, ew.z, fmaf(r1.z, ew.y, r0.z * ew.x)));
+  rr.w = fmaf(r3.w, ew.w, fmaf(r2.w, ew.z, fmaf(r1.w, ew.y, r0.w * ew.x)));
+  return rr;
+}
+template <bool kEns>
 __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B, int N, int n0, int nt, int b, Times times, Scratch sc,
                                                           float* __restrict__ dbg_pre0, int band_rows, int bid0) {
+
   __shared__ uint2 ent_s[kGH][kGW][kSlots];  // the warp's 32 destination lists (4 KB per warp)
   __shared__ float4 par_s[kGH][kGW][2];      // per-destination scalars (1 KB per warp)
   __shared__ float4 rk_s[16][7];             // rank-1 layer-0 weights per 4-channel group (every warp writes the same values)
@@ -1339,6 +1400,19 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
     const float wz_ = wz == 1.0f ? 0.0f : wz;
     const float inv_wz = __fdiv_rn(1.0f, wz);
     const Query qu = make_query(qy, min(x0 + lane, g.WW - 1), g);
+    if constexpr (kEns) {
+      float4(*ens_s)[kGW][2] = ens_table();
+      float ew[4];
+      ensemble_weights(qy, min(x0 + lane, g.WW - 1), g, ew);
+      int idx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Query qk = ensemble_query(qy, min(x0 + lane, g.WW - 1), g, k);
+        idx[k] = qk.iy * g.W + qk.ix;
+      }
+      ens_s[warp][lane][0] = make_float4(__int_as_float(idx[0]), __int_as_float(idx[1]), __int_as_float(idx[2]), __int_as_float(idx[3]));
+      ens_s[warp][lane][1] = make_float4(ew[0], ew[1], ew[2], ew[3]);
+    }
     par_s[warp][lane][0] = make_float4(inv_wz, side.x * inv_wz, side.y * inv_wz, zm);
     par_s[warp][lane][1] = make_float4(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_), __int_as_float(qu.iy * g.W + qu.ix), __int_as_float(live ? cnt_i : -1));
   }
@@ -1365,7 +1439,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       if (i < cnt) y[i] = __ldg(Y4 + (size_t)ent[i].x * 16);
-    const float4 rr = __ldg(R4 + (size_t)__float_as_int(pb.z) * 16);
+    const float4 rr = kEns ? ens_rr(R4, warp, j) : __ldg(R4 + (size_t)__float_as_int(pb.z) * 16);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -1658,6 +1732,7 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   const motif_geom_t& g = a->geom;
   MOTIF_REQUIRE(2ull * g.B * g.HH * g.WW < (1ull << 32), "decode: 2*B*HH*WW must fit 32 bits");
   const int NT = group_size(g.N);
+  const bool ens = a->local_ensemble != 0;  // LunaTokis.local_ensemble (Ours.py:453): four shifted latents per query
   Scratch sc;
   size_t need = 0;
   layout(g.B, NT, g.H, g.W, g.HH, g.WW, &sc, (char*)a->workspace, &need);
@@ -1672,11 +1747,15 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   bool& attr_done = attr_done_dev[current_device_slot()];
   static int n_sm = 148;
   if (!attr_done) {
-    MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
-    MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
+    MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
+    MOTIF_CUDA(cudaFuncSetAttribute(imnet_f16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_i));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
+    MOTIF_CUDA(cudaFuncSetAttribute(flow_bin_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fq));
     MOTIF_CUDA(cudaFuncSetAttribute(synth_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sq));
     const int carve = getenv("MOTIF_GATHER_CARVEOUT") ? atoi(getenv("MOTIF_GATHER_CARVEOUT")) : 50;
-    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    MOTIF_CUDA(cudaFuncSetAttribute(gather_l0_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024));
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
     MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -1724,8 +1803,15 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     {
       if (int rc = trace_select(0, st)) return rc;
       ProfScope prof("imnet_f16_kernel", st);
-      imnet_f16_kernel<<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc, q_begin, q_end);
-      MOTIF_LAUNCHED("imnet_f16_kernel");
+      if (!ens) {
+        imnet_f16_kernel<false><<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc, q_begin, q_end, 0);
+        MOTIF_LAUNCHED("imnet_f16_kernel");
+      } else {
+        for (int k = 0; k < 4; ++k) {  // one pass per shifted latent, accumulated into Y
+          imnet_f16_kernel<true><<<grid128, kThreads, smem_i, st>>>(g, g.B, b, sc, q_begin, q_end, k);
+          MOTIF_LAUNCHED("imnet_f16_kernel");
+        }
+      }
     }
     for (int n0 = a->n_begin; n0 < a->n_end; n0 += NT) {
       const int nt = a->n_end - n0 < NT ? a->n_end - n0 : NT;
@@ -1736,7 +1822,10 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
         if (int rc = trace_select(1, st)) return rc;
         ProfScope prof("flow_bin_f16_kernel", st);
         const int groups = ceil_div((long long)nt * 2 * tiles128, 4);
-        flow_bin_q_kernel<<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n0, nt, b, times, a->alpha, sc, a->flow_out, band);
+        if (!ens)
+          flow_bin_q_kernel<false><<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n0, nt, b, times, a->alpha, sc, a->flow_out, band);
+        else
+          flow_bin_q_kernel<true><<<groups < n_sm ? groups : n_sm, kThreads, smem_fq, st>>>(g, g.B, g.N, n0, nt, b, times, a->alpha, sc, a->flow_out, band);
         MOTIF_LAUNCHED("flow_bin_f16_kernel");
       }
       {
@@ -1746,7 +1835,10 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
         static const int dsmem = getenv("MOTIF_GATHER_DSMEM") ? atoi(getenv("MOTIF_GATHER_DSMEM")) : 0;
         // band mode: the band's blocks are the CTAs [bid0, bid0 + nt * band_blocks) of the whole image's band-major order
         const int bid0 = (by0 / band_rows) * nt * band_rows * blocks_x;
-        gather_l0_kernel<<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, bid0);
+        if (!ens)
+          gather_l0_kernel<false><<<nt * band_blocks, 256, dsmem, st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, bid0);
+        else
+          gather_l0_kernel<true><<<nt * band_blocks, 256, kGH * kGW * 2 * sizeof(float4), st>>>(g, g.B, g.N, n0, nt, b, times, sc, a->dbg_pre0, band_rows, bid0);
         MOTIF_LAUNCHED("gather_l0_kernel");
       }
       {

@@ -54,12 +54,12 @@ class SpaceTimeDecoder:
     def __init__(self, params: Dict[str, torch.Tensor], device="cuda", precision: str = DEFAULT_PRECISION, local_ensemble: bool = False):
         """``local_ensemble``: the reference's ``LunaTokis.local_ensemble`` flag (``Ours.py:453``; ``False`` as shipped).
         ``True`` evaluates every query at four shifted latents and blends them by the diagonally swapped area weights
-        (``Ours.py:660-663, 754-764``); implemented by ``precision='fp32'`` only."""
+        (``Ours.py:660-663, 754-764``); implemented by ``precision='f16x3'`` (four tensor-core passes) and ``'fp32'``."""
         _lib.load()  # fail loudly when the CUDA library is missing
         if precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {list(PRECISIONS)}")
-        if local_ensemble and precision != "fp32":
-            raise NotImplementedError("local_ensemble=True is implemented by precision='fp32' (the shipped checkpoint runs with it off, Ours.py:453)")
+        if local_ensemble and precision == "tf32x3":
+            raise NotImplementedError("local_ensemble=True is implemented by precision='f16x3' and 'fp32' (the shipped checkpoint runs with it off, Ours.py:453)")
         self.local_ensemble = bool(local_ensemble)
         self.device = torch.device(device)
         if self.device.type != "cuda":

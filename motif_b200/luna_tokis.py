@@ -84,12 +84,12 @@ def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, tra
         # share this dict and each finds (or builds, from ITS OWN parameters) the decoder of the device it runs on.
         cache = self.__dict__.setdefault("_motif_decoders", {})
         sd_version = sum(p._version for p in self.parameters())
-        ens = bool(getattr(self, "local_ensemble", False))  # Ours.py:453; the four-latent ensemble runs on the fp32 path
+        ens = bool(getattr(self, "local_ensemble", False))  # Ours.py:453
         key = (feat.device.type, feat.device.index)
         hit = cache.get(key)
         if hit is None or hit[1] != sd_version or hit[0].local_ensemble != ens:
             dec = SpaceTimeDecoder.from_state_dict(self.state_dict(), device=feat.device, local_ensemble=ens,
-                                                   precision="fp32" if ens else getattr(self, "_motif_precision", "f16x3"))
+                                                   precision=getattr(self, "_motif_precision", "f16x3"))
             cache[key] = (dec, sd_version)
         dec = cache[key][0]
         rgb, flow_out = dec.decode(feat.float(), flow_feat.float(), residual.float(), tt, (HH, WW))

@@ -69,14 +69,15 @@ def test_decoder_vs_reference_golden(case, precision):
     assert p > PSNR_MIN
 
 
-def test_local_ensemble_vs_reference_golden():
+@pytest.mark.parametrize("precision", ["fp32", "f16x3"])
+def test_local_ensemble_vs_reference_golden(precision):
     """LunaTokis.local_ensemble = True (Ours.py:660-663, 754-764; off as shipped): four shifted latents blended by the
     diagonally swapped area weights.  Golden = the reference's own forward with the flag set (oracle/make_golden.py)."""
     from motif_b200.decoder import SpaceTimeDecoder
 
     g = load_golden("decoder_ens_x3")
     HH, WW = [int(v) for v in g["hr_size"]]
-    dec = SpaceTimeDecoder(hot_params(g), device="cuda", precision="fp32", local_ensemble=True)
+    dec = SpaceTimeDecoder(hot_params(g), device="cuda", precision=precision, local_ensemble=True)
     rgb, flow = dec.decode(g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
     assert rgb.shape == g["out"].shape and flow.shape == g["flow_out"].shape
     d_flow = (flow.cpu() - g["flow_out"]).abs().max().item()
@@ -86,7 +87,7 @@ def test_local_ensemble_vs_reference_golden():
     assert d_rgb < TOL, d_rgb
     assert p > PSNR_MIN
     # the flag changes the function: the single-latent decode of the same inputs is far from this golden
-    plain, _ = SpaceTimeDecoder(hot_params(g), device="cuda", precision="fp32").decode(
+    plain, _ = SpaceTimeDecoder(hot_params(g), device="cuda", precision=precision).decode(
         g["feat"].cuda(), g["flow_feat"].cuda(), g["residual"].cuda(), g["target_t"], (HH, WW))
     assert (plain.cpu() - g["out"]).abs().max().item() > 5e-3
 
@@ -113,11 +114,11 @@ def test_weight_images_are_reused_and_two_decoders_do_not_mix():
     assert (a1 - a3).abs().max().item() < 1e-2  # same function in exact fp32 (unstable-count pixels aside)
 
 
-def test_local_ensemble_needs_fp32():
+def test_local_ensemble_is_refused_by_the_first_generation_path():
     from motif_b200.decoder import SpaceTimeDecoder
 
     with pytest.raises(NotImplementedError):
-        SpaceTimeDecoder(decoder_ref.random_params(0), device="cuda", precision="f16x3", local_ensemble=True)
+        SpaceTimeDecoder(decoder_ref.random_params(0), device="cuda", precision="tf32x3", local_ensemble=True)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
