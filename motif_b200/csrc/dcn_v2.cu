@@ -130,6 +130,11 @@ __global__ void __launch_bounds__(kDcnThreads, 4) dcn_v2_fwd_kernel(const float*
   }
 }
 
+// tcgen05 implicit GEMM for the model's configuration (dcn_v2_tc.cu)
+bool dcn_v2_tc_applicable(int Cin, int Cout, int dg);
+int dcn_v2_tc_fwd(const float* in, const float* offset, const float* mask, const float* weight, const float* bias, float* out, int B, int H, int W,
+                  cudaStream_t st);
+
 }  // namespace motif
 
 using namespace motif;
@@ -141,6 +146,7 @@ extern "C" int motif_dcn_v2_fwd(const float* in, const float* offset, const floa
   MOTIF_REQUIRE(Cin % deformable_groups == 0, "dcn_v2: C_in=%d not divisible by deformable_groups=%d", Cin, deformable_groups);
   MOTIF_REQUIRE(Cin / deformable_groups <= kDcnMaxCpg, "dcn_v2: more than %d channels per deformable group", kDcnMaxCpg);
   MOTIF_REQUIRE((long long)B * H * W < (1LL << 31) && (long long)H * W < (1LL << 30), "dcn_v2: image too large");
+  if (dcn_v2_tc_applicable(Cin, Cout, deformable_groups)) return dcn_v2_tc_fwd(in, offset, mask, weight, bias, out, B, H, W, (cudaStream_t)stream);
   dim3 grid(ceil_div((long long)B * H * W, kDcnPx), ceil_div(Cout, kDcnCo));
   ProfScope prof("dcn_v2_fwd_kernel", (cudaStream_t)stream);
   dcn_v2_fwd_kernel<<<grid, kDcnThreads, 0, (cudaStream_t)stream>>>(in, offset, mask, weight, bias, out, B, Cin, Cout, H, W, deformable_groups);

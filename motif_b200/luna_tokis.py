@@ -28,7 +28,7 @@ import types
 import torch
 from torch.nn.functional import interpolate
 
-from . import alt_cuda_corr
+from . import alt_cuda_corr, dcn_v2
 from .decoder import SpaceTimeDecoder, hr_size_from_scale
 from .flow_front import flow_front
 from .softsplat_count_cp import Softsplat_Count
@@ -96,12 +96,16 @@ def forward_b200(self, x, input_target_frames, target_t, scale=None, rank=0, tra
     return rgb, flow_out, 0.0  # Ours.py:580, 858: flow_GT = 0 on the inference path, returned as (0 / 20.0) / (HH / H)
 
 
-def install(model, precision: str = "f16x3", raft_lookup: bool = True):
+def install(model, precision: str = "f16x3", raft_lookup: bool = True, dcn: bool = True):
     """Patch a reference ``LunaTokis`` instance in place and return it.  ``raft_lookup``: answer the reference's
     ``import alt_cuda_corr`` (``models/core/corr.py:5, 82`` -- a binary it does not ship) with ``motif_b200.alt_cuda_corr``,
-    so that the shipped ``alternate_corr=True`` RAFT (``Ours.py:417-430``) runs without materialising the all-pairs volume."""
+    so that the shipped ``alternate_corr=True`` RAFT (``Ours.py:417-430``) runs without materialising the all-pairs volume.
+    ``dcn``: rebind ``dcn_v2_conv`` of an imported reference ``DCNv2.dcn_v2`` module (the encoder's ``DCN_sep`` layers,
+    ``Ours.py:53-172``) to the tcgen05 implicit GEMM of ``motif_b200.dcn_v2``."""
     if raft_lookup:
         alt_cuda_corr.install()
+    if dcn:
+        dcn_v2.install()
     object.__setattr__(model, "_motif_precision", precision)
     model.fwarp = Softsplat()
     model.fwarp_max = Softsplat_Max()

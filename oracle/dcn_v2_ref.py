@@ -41,9 +41,9 @@ def dcn_v2_conv(inp, offset, mask, weight, bias, stride=1, padding=1, dilation=1
     Ho = (H + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
     Wo = (W + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
     cpg = Cin // deformable_groups
-    hs = (torch.arange(Ho) * stride - padding).view(Ho, 1).float()
-    ws = (torch.arange(Wo) * stride - padding).view(1, Wo).float()
-    cols = torch.zeros(B, Cin, kh * kw, Ho, Wo)
+    hs = (torch.arange(Ho) * stride - padding).view(Ho, 1).to(inp.dtype)
+    ws = (torch.arange(Wo) * stride - padding).view(1, Wo).to(inp.dtype)
+    cols = torch.zeros(B, Cin, kh * kw, Ho, Wo, dtype=inp.dtype)
     for b in range(B):
         for g in range(deformable_groups):
             plane = inp[b, g * cpg:(g + 1) * cpg]

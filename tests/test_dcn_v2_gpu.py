@@ -33,6 +33,47 @@ def test_vs_oracle(shape, sigma):
     assert (out - ref).abs().max().item() < 2e-5 * (1.0 + ref.abs().max().item())
 
 
+@pytest.mark.parametrize("scale_x,scale_w,scale_m", [(1.0, 1.0, 1.0), (3.0e-5, 1.0, 1.0), (2.0e4, 1.0e-3, 1.0), (1.0, 50.0, 6.0)])
+def test_tensor_core_path_ranges_and_ragged_tiles(scale_x, scale_w, scale_m):
+    """The tcgen05 path (64 -> 64, 8 groups): two images whose 442 pixels do not fill the 128-pixel tiles (one tile straddles
+    the batch boundary), no bias, and operand magnitudes far from 1 -- the power-of-two operand scaling must keep the two-piece
+    fp16 split at fp32 accuracy whatever the ranges (relative gate)."""
+    from motif_b200.dcn_v2 import dcn_v2_conv
+
+    x, off, m, w, b = _case(2, 64, 64, 13, 17, 8, 2.0, seed=77)
+    x, w, m = x * scale_x, w * scale_w, m * scale_m
+    ref = dcn_v2_ref.dcn_v2_conv(x.double(), off.double(), m.double(), w.double(), torch.zeros(64, dtype=torch.float64), 1, 1, 1, 8).float()
+    with torch.no_grad():
+        out = dcn_v2_conv(x.cuda(), off.cuda(), m.cuda(), w.cuda(), None, 1, 1, 1, 8).cpu()
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+
+
+def test_tensor_core_path_matches_cuda_core_path():
+    """Same inputs through both kernels of motif_dcn_v2_fwd (the fused CUDA-core kernel serves every other shape)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import torch, sys; sys.path.insert(0, '.'); from motif_b200.dcn_v2 import dcn_v2_conv\n"
+        "g = torch.Generator().manual_seed(5)\n"
+        "x = torch.randn(1, 64, 45, 80, generator=g); off = torch.randn(1, 144, 45, 80, generator=g) * 1.5\n"
+        "m = torch.sigmoid(torch.randn(1, 72, 45, 80, generator=g)); w = torch.randn(64, 64, 3, 3, generator=g) / 24; b = torch.randn(64, generator=g)\n"
+        "with torch.no_grad(): out = dcn_v2_conv(x.cuda(), off.cuda(), m.cuda(), w.cuda(), b.cuda(), 1, 1, 1, 8).cpu()\n"
+        "torch.save(out, sys.argv[1])\n")
+    import os
+    import tempfile
+
+    outs = []
+    for simt in ("0", "1"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=dict(os.environ, MOTIF_DCN_SIMT=simt), cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            outs.append(torch.load(f.name))
+    assert (outs[0] - outs[1]).abs().max().item() < 2e-5 * (1.0 + outs[1].abs().max().item())
+    assert not torch.equal(outs[0], outs[1])  # two different kernels did run
+
+
 def test_zero_offsets_equal_plain_convolution():
     from motif_b200.dcn_v2 import dcn_v2_conv
 
