@@ -28,7 +28,7 @@ import types
 import torch
 from torch.nn.functional import interpolate
 
-from . import alt_cuda_corr, dcn_v2
+from . import alt_cuda_corr, dcn_v2, raft_schedule
 from .decoder import SpaceTimeDecoder, hr_size_from_scale
 from .flow_front import flow_front
 from .softsplat_count_cp import Softsplat_Count
@@ -56,7 +56,9 @@ def surround(self, x, target_t, scale, iter=12, front=flow_front):
         # HR input motion from the pretrained RAFT on the pairs 00, 01, 10, 11 (Ours.py:540-555)
         x_norm = interpolate(x.reshape(B, -1, H, W), size=(HH, WW), mode="bilinear", align_corners=False).reshape(B, -1, 2, HH, WW)
         fr0, fr1 = x_norm[:, :, 0], x_norm[:, :, 1]
-        flow = self.flow_predictor(torch.cat([fr0, fr0, fr1, fr1], dim=0) * 255.0, torch.cat([fr0, fr1, fr0, fr1], dim=0) * 255.0, iters=iter)[-1]
+        # (raft_schedule: only the pairs 01 and 10 are estimated -- the reference zeroes 00 and 11 right below -- and the
+        #  feature encoder runs once per distinct frame)
+        flow = raft_schedule.four_pair_flows(self.flow_predictor, fr0, fr1, iter)
         fr0, fr1 = x[:, :, 0], x[:, :, 1]
         flow = interpolate(flow, size=(H, W), mode="bilinear", align_corners=False) * (H / HH)
         flow = flow.reshape(4, B, 2, H, W)

@@ -87,3 +87,109 @@ def test_install_rebinds_the_reference_import():
     finally:
         del sys.modules["models.core.corr"]
         sys.modules.pop("alt_cuda_corr", None)
+
+
+def test_lookup_block_equals_the_oracle_block():
+    """``raft_schedule.LookupBlock`` (AlternateCorrBlock with the layout changes hoisted out of the iteration loop) against the
+    oracle's restatement of ``CorrBlock`` (pinned by the reference's own class, tests/golden/raft_corr.npz); called twice with
+    different coordinates, as the RAFT iteration does."""
+    from motif_b200.raft_schedule import LookupBlock
+
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 2, 128, 24, 40
+    f1, f2 = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    block = LookupBlock(f1.cuda(), f2.cuda(), radius=3)
+    for k in range(2):
+        coords = torch.stack([xs, ys])[None].repeat(B, 1, 1, 1) + torch.randn(B, 2, H, W, generator=g) * (2.0 + 3.0 * k)
+        ref = raft_corr_ref.corr_block_lookup(f1, f2, coords, 4, 3)
+        out = block(coords.cuda()).cpu()
+        assert out.shape == ref.shape == (B, 4 * 49, H, W)
+        assert (out - ref).abs().max().item() < 2e-4 * (1.0 + ref.abs().max().item())
+
+
+def test_flow_two_pairs_runs_raft_sub_modules_on_cuda():
+    """The schedule's glue on the device with a RAFT-shaped stand-in (the reference checkout is absent on the GPU box; bit-equality
+    with the unmodified ``RAFT.forward`` is pinned on the CPU, tests/test_host_logic.py): the stand-in's own four-pair forward
+    (written like raft.py:86-144, lookups through the oracle's block) and ``four_pair_flows`` must agree on the pairs 01 / 10."""
+    import sys
+    import types
+
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    from motif_b200 import raft_schedule
+
+    class Update(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c = nn.Conv2d(4 * 49 + 2 + 16 + 16, 16 + 2, 3, padding=1)
+
+        def forward(self, net, inp, corr, flow):
+            y = self.c(torch.cat([net, inp, corr, flow], 1))
+            return torch.tanh(y[:, :16]), None, 0.5 * torch.tanh(y[:, 16:])
+
+    class Enc(nn.Module):
+        def __init__(self, o):
+            super().__init__()
+            self.c = nn.Conv2d(3, o, 8, stride=8)
+            self.n = nn.InstanceNorm2d(o)
+
+        def forward(self, x):
+            is_list = isinstance(x, (list, tuple))
+            if is_list:
+                bd = x[0].shape[0]
+                x = torch.cat(x, 0)
+            y = self.n(self.c(x))
+            return torch.split(y, [bd, bd], 0) if is_list else y
+
+    mod = types.ModuleType("fake_raft_module")
+
+    class FakeRaft(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.args = types.SimpleNamespace(mixed_precision=False, alternate_corr=True, corr_radius=3)
+            self.hidden_dim, self.context_dim = 16, 16
+            self.fnet, self.cnet, self.update_block = Enc(128), Enc(32), Update()
+
+        def initialize_flow(self, img):
+            n, _, h, w = img.shape
+            ys, xs = torch.meshgrid(torch.arange(h // 8, device=img.device).float(), torch.arange(w // 8, device=img.device).float(), indexing="ij")
+            c = torch.stack([xs, ys])[None].repeat(n, 1, 1, 1)
+            return c, c.clone()
+
+        def upsample_flow(self, flow, mask):
+            raise AssertionError("no mask in this stand-in")
+
+        def forward(self, image1, image2, iters=12):
+            image1, image2 = 2 * (image1 / 255.0) - 1.0, 2 * (image2 / 255.0) - 1.0
+            fmap1, fmap2 = self.fnet([image1.contiguous(), image2.contiguous()])
+            cnet = self.cnet(image1)
+            net, inp = torch.tanh(cnet[:, :16]), torch.relu(cnet[:, 16:])
+            coords0, coords1 = self.initialize_flow(image1)
+            preds = []
+            for _ in range(iters):
+                corr = raft_corr_ref.corr_block_lookup(fmap1.cpu(), fmap2.cpu(), coords1.cpu(), 4, 3).to(image1.device)
+                net, _m, delta = self.update_block(net, inp, corr, coords1 - coords0)
+                coords1 = coords1 + delta
+                preds.append(mod.upflow8(coords1 - coords0))
+            return preds
+
+    FakeRaft.__module__ = "fake_raft_module"
+    mod.autocast = torch.cuda.amp.autocast
+    mod.upflow8 = lambda flow: 8 * F.interpolate(flow, size=(8 * flow.shape[2], 8 * flow.shape[3]), mode="bilinear", align_corners=True)
+    sys.modules["fake_raft_module"] = mod
+    try:
+        torch.manual_seed(2)
+        raft = FakeRaft().cuda().eval()
+        assert raft_schedule.is_raft(raft)
+        low = torch.rand(2, 3, 24, 40)  # 24x40 features: the coarsest of the four levels is 3x5 (CorrBlock divides by H - 1)
+        fr0, fr1 = [t.cuda() for t in F.interpolate(low, size=(192, 320), mode="bilinear", align_corners=False).split(1)]
+        with torch.no_grad():
+            four = raft(torch.cat([fr0, fr0, fr1, fr1]) * 255.0, torch.cat([fr0, fr1, fr0, fr1]) * 255.0, iters=3)[-1]
+            sched = raft_schedule.four_pair_flows(raft, fr0, fr1, 3)
+        assert sched.shape == four.shape == (4, 2, 192, 320) and torch.isfinite(four).all()
+        assert not sched[0].any() and not sched[3].any()
+        assert (sched[1:3] - four[1:3]).abs().max().item() < 1e-3 * (1.0 + four.abs().max().item())
+    finally:
+        del sys.modules["fake_raft_module"]
