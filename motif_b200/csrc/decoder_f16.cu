@@ -558,6 +558,42 @@ __device__ __forceinline__ f32x2 fsub2(f32x2 a, f32x2 b) {
   return d;
 }
 
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// Two sines on the FMA pipe (packed fp32): the MLP epilogues keep the XU pipe (MUFU.SIN, 16 / clk / SM) saturated whenever the
+// four tile slots of an SM are in their sine phases together while issue slots are free, so every MOTIF_SIN_POLY-th pair of
+// hidden units takes this route instead.  x / (2 pi) is reduced to f in [-0.5, 0.5] with an exact fma remainder (the same
+// single-constant reduction FMUL.RZ + MUFU.SIN performs), sin(2 pi f) = f * P(f^2), degree 13: 5e-7 max abs error in fp32
+// arithmetic against 4.8e-7 for MUFU.SIN.
+#ifndef MOTIF_SIN_POLY
+#define MOTIF_SIN_POLY 0
+#endif
+__device__ __forceinline__ f32x2 sin_poly2(f32x2 x) {
+  const f32x2 inv = pack2(0.15915494309189535f, 0.15915494309189535f), magic = pack2(12582912.0f, 12582912.0f);
+  const f32x2 t = ffma2(x, inv, magic);
+  const f32x2 nk = fsub2(magic, t);  // -rint(x / 2 pi)
+  const f32x2 f = ffma2(x, inv, nk);
+  const f32x2 u = fmul2(f, f);
+  f32x2 p = pack2(3.1996936798095703f, 3.1996936798095703f);
+  p = ffma2(p, u, pack2(-14.868611335754395f, -14.868611335754395f));
+  p = ffma2(p, u, pack2(42.01616668701172f, 42.01616668701172f));
+  p = ffma2(p, u, pack2(-76.70155334472656f, -76.70155334472656f));
+  p = ffma2(p, u, pack2(81.60502624511719f, 81.60502624511719f));
+  p = ffma2(p, u, pack2(-41.341697692871094f, -41.341697692871094f));
+  p = ffma2(p, u, pack2(6.2831854820251465f, 6.2831854820251465f));
+  return fmul2(p, f);
+}
+// sine of a packed pair: MUFU.SIN twice, or the FMA-pipe polynomial for every MOTIF_SIN_POLY-th pair
+__device__ __forceinline__ f32x2 sin_pair(f32x2 arg, int pr) {
+  if (MOTIF_SIN_POLY > 0 && (pr % (MOTIF_SIN_POLY > 0 ? MOTIF_SIN_POLY : 1)) == (MOTIF_SIN_POLY > 0 ? MOTIF_SIN_POLY : 1) - 1) return sin_poly2(arg);
+  float a0, a1;
+  unpack2(arg, a0, a1);
+  return pack2(__sinf(a0), __sinf(a1));
+}
+
 // fp32 pair -> fp16 hi pair + fp16 lo pair (lo = fp16 of the exact fp32 remainder)
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -897,14 +933,16 @@ __device__ __forceinline__ void q_issuer_dyn(QBars& bars, const unsigned char* i
 
 struct QEpi {
   QBars* bars;
+  bool wait_v1;  // accumulator waits through the first-generation retry loop (a compile-time constant of the kernel, see q_take_d)
   int tile, quad;
   uint32_t lane_addr;  // TMEM address of this thread's lane, column 0 of its tile
   uint32_t ph_d;
 };
-__device__ __forceinline__ QEpi q_make_epi(QBars& bars) {
+__device__ __forceinline__ QEpi q_make_epi(QBars& bars, bool wait_v1) {
   const int w = (threadIdx.x >> 5) - kEpiWarp0;
   QEpi c;
   c.bars = &bars;
+  c.wait_v1 = wait_v1;
   c.tile = w >> 2;
   c.quad = w & 3;
   c.lane_addr = c.tile * kQTileCols + ((uint32_t)(c.quad * 32) << 16);
@@ -917,8 +955,14 @@ __device__ __forceinline__ QEpi q_make_epi(QBars& bars) {
 #define TRACE_Q(c, k) do { } while (0)
 #endif
 // all 64 accumulator columns of this thread's row into registers
+// The retry loop of this wait is chosen per kernel by measurement (same box, same run): flow_bin_q 2.32 ms with the
+// first-generation loop (twelve instructions per failed try) against 2.43 ms with the lean one, synth_q 1.01 against 0.99 ms --
+// how fast the waiting epilogue warps of a slot re-poll shifts the phase in which the four slots of an SM meet on the MUFU pipe.
 __device__ __forceinline__ void q_take_d(QEpi& c, uint32_t (&r)[64], bool release) {
-  mbar_wait(&c.bars->d_ready[c.tile], c.ph_d);
+  if (c.wait_v1)
+    mbar_wait_v1(&c.bars->d_ready[c.tile], c.ph_d);
+  else
+    mbar_wait(&c.bars->d_ready[c.tile], c.ph_d);
   c.ph_d ^= 1;
   tc_fence_after();
   TRACE_Q(c, 10);
@@ -1030,9 +1074,7 @@ __device__ __forceinline__ void q_sine_out3_c(QEpi& c, float s, int ch, bool rel
 #pragma unroll
   for (int pr = 0; pr < 32; ++pr) {
     const ulonglong2 wa = w2[2 * pr], wb = w2[2 * pr + 1];
-    float a0, a1;
-    unpack2(ffma2(pack2(__uint_as_float(r[2 * pr]), __uint_as_float(r[2 * pr + 1])), s2, wa.x), a0, a1);
-    const f32x2 v = pack2(__sinf(a0), __sinf(a1));
+    const f32x2 v = sin_pair(ffma2(pack2(__uint_as_float(r[2 * pr]), __uint_as_float(r[2 * pr + 1])), s2, wa.x), pr);
     p0[pr & 1] = ffma2(v, wa.y, p0[pr & 1]);
     p1[pr & 1] = ffma2(v, wb.x, p1[pr & 1]);
     p2[pr & 1] = ffma2(v, wb.y, p2[pr & 1]);
@@ -1191,7 +1233,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
   } else if (warp == 3) {
     q_issuer_dyn<3>(sm.bars, &sm.img[0][0], kQProgF);
   } else {
-    QEpi c = q_make_epi(sm.bars);
+    QEpi c = q_make_epi(sm.bars, true);
 #ifdef MOTIF_OUT3_SMEM
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 320);
 #endif
@@ -1551,7 +1593,7 @@ __global__ void __launch_bounds__(kThreads, 1) synth_q_kernel(motif_geom_t g, in
   } else if (warp == 3) {
     q_issuer_dyn<3>(sm.bars, &sm.img[0][0], kQProgS);
   } else {
-    QEpi c = q_make_epi(sm.bars);
+    QEpi c = q_make_epi(sm.bars, false);
 #ifdef MOTIF_OUT3_SMEM
     const float4* cw = reinterpret_cast<const float4*>(sm.consts + 128);
 #endif
@@ -1759,10 +1801,6 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
     int dev = 0;
     MOTIF_CUDA(cudaGetDevice(&dev));
     MOTIF_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    if (getenv("MOTIF_MBAR_HINT")) {
-      const uint32_t hint = (uint32_t)atoi(getenv("MOTIF_MBAR_HINT"));
-      MOTIF_CUDA(cudaMemcpyToSymbol(tc::c_mbar_hint, &hint, sizeof(hint)));
-    }
     attr_done = true;
   }
   // arm the destination accumulators (a no-op when the previous decode on this workspace completed, see arm_kernel)

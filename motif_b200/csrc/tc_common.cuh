@@ -21,17 +21,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~the hint
-// elapses, instead of burning issue slots that the working warps of the same scheduler need.
-static __constant__ uint32_t c_mbar_hint = 100000u;  // per translation unit; tuning hook
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or a hardware time limit
+// elapses, instead of burning issue slots that the working warps of the same scheduler need.  (The hint is an immediate: values
+// from 10 ns to 100 us measured alike, and a constant-bank operand cost one load per failed try.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 100000;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(c_mbar_hint)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
@@ -51,6 +51,8 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 // trap (reported as a CUDA error) instead of a hung GPU.  Debug aid: when a host-mapped buffer has been installed
 // (motif_tc_set_wait_debug), a thread whose wait expires first records (barrier address, parity, block, thread) there --
 // host memory survives the trap -- and keeps waiting a little longer so that the other stuck threads can record too.
+// The retry loop is the hot part (a failed try is ~12 % of the instructions the MLP kernels issue): one counter update and
+// one branch per failed try; everything else lives in the out-of-line expiry path.
 static __device__ unsigned int* g_wait_dbg = nullptr;  // per translation unit
 static __device__ __noinline__ void mbar_wait_expired(uint64_t* bar, uint32_t parity) {
   if (g_wait_dbg != nullptr) {
@@ -63,12 +65,43 @@ static __device__ __noinline__ void mbar_wait_expired(uint64_t* bar, uint32_t pa
     }
     __threadfence_system();
   }
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 16); ++it)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+// first-generation wait loop (constant-bank hint, two counter tests per failed try): kept selectable, see mbar_wait_sel
+static __constant__ uint32_t c_mbar_hint = 100000u;
+__device__ __forceinline__ bool mbar_try_wait_c(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(c_mbar_hint)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_v1(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait_c(bar, parity); ++it) {
     if (it == (1u << 20)) mbar_wait_expired(bar, parity);
     if (it > (1u << 20) + (1u << 16)) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t left = 1u << 20;
+#pragma unroll 1
+  do {
+    if (--left == 0u) {
+      mbar_wait_expired(bar, parity);
+      return;
+    }
+#if defined(MOTIF_WAIT_BACKOFF) && MOTIF_WAIT_BACKOFF > 0
+    __nanosleep(MOTIF_WAIT_BACKOFF);
+#endif
+  } while (!mbar_try_wait(bar, parity));
 }
 
 // ---- 1-D bulk async copy global -> shared, completion on an mbarrier (no tensor map needed) --------------
