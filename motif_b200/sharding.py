@@ -39,6 +39,28 @@ def partition_rows(n_rows: int, world_size: int, align: int = 16) -> List[Tuple[
     return out
 
 
+def slice_plan(sizes, world_size: int, rank: int):
+    """Sliced copy-in of a clip every rank can read (pinned host memory of the node): the flat latent buffer
+    ``[feat | flow_feat | residual]`` is padded to ``per * world_size`` elements and rank ``r`` fills ``[r * per, (r + 1) * per)``
+    over its own PCIe link before an in-place all-gather.  Returns ``(per, [(tensor index, src begin, src end, dst begin)])``."""
+    total = int(sum(sizes))
+    per = (total + world_size - 1) // world_size
+    lo, hi, off, parts = rank * per, (rank + 1) * per, 0, []
+    for i, n in enumerate(sizes):
+        a, b = max(lo, off), min(hi, off + int(n))
+        if b > a:
+            parts.append((i, a - off, b - off, a))
+        off += int(n)
+    return per, parts
+
+
+def all_gather_slices(flat: torch.Tensor, per: int, group=None):
+    """In-place all-gather of the ranks' slices of ``flat`` (``per * world_size`` elements; NCCL over NVLink, gloo in CPU tests)."""
+    r = dist.get_rank(group)
+    dist.all_gather_into_tensor(flat, flat[r * per:(r + 1) * per].clone() if flat.device.type == "cpu" else flat[r * per:(r + 1) * per], group=group)
+    return flat
+
+
 def check_halo(flow_y_max: torch.Tensor, halo: int, group=None) -> float:
     """Largest ``|flow_y|`` (HR pixels) any rank saw among the sources of its own band -- every source row belongs to exactly
     one band, so this is the maximum over the frame.  A band decode with this ``halo`` was exact iff the value is below

@@ -100,6 +100,26 @@ def _halo_worker(rank, world, port):
         dist.destroy_process_group()
 
 
+def _slice_worker(rank, world, port):
+    import torch.distributed as dist
+
+    from motif_b200 import sharding, synthetic
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        hosts = synthetic.synthetic_latents(1, 5, 7, seed=8)  # every rank can read the clip; 11 200 floats do not divide by 3
+        sizes = [t.numel() for t in hosts]
+        per, parts = sharding.slice_plan(sizes, world, rank)
+        flat = torch.full((per * world,), float("nan"))
+        for i, a, b, dst in parts:
+            flat[dst:dst + (b - a)].copy_(hosts[i].reshape(-1)[a:b])
+        assert sum(b - a for _, a, b, _ in parts) <= per
+        sharding.all_gather_slices(flat, per)
+        assert torch.equal(flat[:sum(sizes)], torch.cat([t.reshape(-1) for t in hosts]))
+    finally:
+        dist.destroy_process_group()
+
+
 def _exchange_worker(rank, world, port):
     import torch.distributed as dist
 
@@ -125,6 +145,11 @@ def _exchange_worker(rank, world, port):
 
 def test_two_rank_gloo_latent_exchange_pipeline():
     mp.spawn(_exchange_worker, args=(2, _free_port()), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_sliced_copy_in_and_all_gather(world):
+    mp.spawn(_slice_worker, args=(world, _free_port()), nprocs=world, join=True)
 
 
 def test_two_rank_gloo_halo_check():
