@@ -51,8 +51,8 @@ def load_peaks():
 
 def load_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed
-    `ncu --set full` capture of this workload (profiles/r1_traffic.json; written by tools/ncu_traffic.py)."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    `ncu --set full` capture of this workload (profiles/r2_traffic.json; written by tools/ncu_traffic.py)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(path):
         with open(path) as f:
             return json.load(f).get("traffic_bytes_per_launch", {})
@@ -341,10 +341,12 @@ def main():
     # ---- roofline of the dominant kernel of the step (per launch, CUDA events on the launch stream) ----
     # Algorithmic work per launch.  Tensor-bound kernels: dense MACs of the reference's layers
     # counted ONCE (the three split-product passes are not extra algorithmic FLOPs, so an error-compensated path
-    # cannot exceed 1/3 of the peak by construction).  HBM-bound kernel (gather_l0): bytes every destination pixel
-    # must move once -- 2 source rows (one per reference frame, 256 B each), its list entries (8 x 8 B on average),
-    # side/zmax/count read + re-arm (48 B), the 256-byte fp16 hi/lo A operand written for synth_net.
-    GATHER_BYTES_PER_DST = 2 * 256 + 64 + 48 + 256
+    # cannot exceed 1/3 of the peak by construction).  HBM-bound kernel (gather_l0), bytes that MUST cross HBM per destination
+    # pixel and timestamp: its list entries (8 x 8 B on average), side/zmax/count read + re-arm (48 B), the 256-byte fp16
+    # hi/lo A operand written for synth_net, and the per-source rows of both reference frames (2 x 256 B) ONCE PER CLIP -- the
+    # timestamps of a group share them through L2 (band-major CTA order) -- i.e. 512 / N bytes per timestamp.  (Round 1
+    # counted the rows once per timestamp, 880 B, which exceeded the measured DRAM traffic and flattered the kernel.)
+    GATHER_BYTES_PER_DST = 64 + 48 + 256 + (2 * 256) / N
     work = {
         "imnet_kernel": ("tensor", FLOP_IMNET_ROW * 2 * B * qs), "imnet_tc_kernel": ("tensor", FLOP_IMNET_ROW * 2 * B * qs),
         "flow_splat_kernel": ("tensor", FLOP_FLOW_IMNET_ROW * 2 * qs), "flow_splat_tc_kernel": ("tensor", FLOP_FLOW_IMNET_ROW * 2 * qs),
@@ -382,7 +384,7 @@ def main():
         kd = kernels[dom]
         peak = tensor_peak if kd["bound"] == "tensor" else peaks["hbm_gbs"]
         note = (f"{peak_name}, {peaks['source']}; algorithmic FLOPs (K un-padded, one pass counted; 3 split-product passes run)" if kd["bound"] == "tensor"
-                else f"HBM copy bandwidth, {peaks['source']}; {GATHER_BYTES_PER_DST} algorithmic bytes per destination pixel")
+                else f"HBM copy bandwidth, {peaks['source']}; {GATHER_BYTES_PER_DST:.0f} algorithmic bytes per destination pixel and timestamp")
         roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": peak, "unit": kd["unit"], "frac": kd["frac"],
                     "traffic": kd["traffic"], "peak_note": note}
         step_flops = (2 * FLOP_FLOW_IMNET_ROW + FLOP_SYNTH_ROW) * N * qs + FLOP_IMNET_ROW * 2 * B * qs
@@ -414,8 +416,10 @@ def main():
     op_ms = s0.elapsed_time(s1) / reps
     gather_ms = sp["splat_gather_kernel"][0] / max(sp["splat_gather_kernel"][1], 1)
     alg_bytes = SPLAT_BYTES_PER_SRC * qs
-    roofline_splat = {"kernel": "splat_gather_kernel", "bound": "hbm", "achieved": alg_bytes / (gather_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                      "frac": alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("splat_gather_kernel"),
+    # `frac` is the OPERATOR (bin + gather + surplus launches + memset, as a caller of FunctionSoftsplat sees it); the gather kernel alone is kernel_frac
+    roofline_splat = {"kernel": "FunctionSoftsplat operator (splat_bin + splat_gather + surplus)", "bound": "hbm", "achieved": alg_bytes / (op_ms * 1e-3) / 1e9,
+                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / (op_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": traffic.get("splat_gather_kernel"),
+                      "kernel_gbs": alg_bytes / (gather_ms * 1e-3) / 1e9, "kernel_frac": alg_bytes / (gather_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                       "operator_gbs": alg_bytes / (op_ms * 1e-3) / 1e9, "operator_ms": op_ms,
                       "bin_ms": sp["splat_bin_kernel"][0] / max(sp["splat_bin_kernel"][1], 1),
                       "note": f"FunctionSoftsplat softmax, [1,130,{HH},{WW}], 1056 B per source pixel; {peaks['source']}"}

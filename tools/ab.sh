@@ -15,7 +15,7 @@ import json, sys
 d = json.load(open(f"gpurun_out/ab_{sys.argv[1]}.json"))
 print("ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["ms_per_step"], 3), "clocks", d["clocks"]["sm_mhz"])
 print({k: round(v["avg_ms"], 3) for k, v in d["kernels"].items()})
-print("splat op", round(d["roofline_splat"]["operator_ms"], 3), "ms, gather frac", round(d["roofline_splat"]["frac"], 3))
+print("splat op", round(d["roofline_splat"]["operator_ms"], 3), "ms, operator frac", round(d["roofline_splat"]["frac"], 3), "gather kernel frac", round(d["roofline_splat"]["kernel_frac"], 3))
 PY
   for kv in $envs; do unset "${kv%%=*}"; done
   i=$((i+1))

@@ -11,7 +11,7 @@ try:
     d = json.load(open("gpurun_out/${tag}_bench.json"))
     print("ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["ms_per_step"], 3), "clocks", d["clocks"]["sm_mhz"])
     print({k: round(v["avg_ms"], 3) for k, v in d["kernels"].items()})
-    print("splat", round(d["roofline_splat"]["operator_ms"], 3), "ms, gather frac", round(d["roofline_splat"]["frac"], 3))
+    print("splat", round(d["roofline_splat"]["operator_ms"], 3), "ms, operator frac", round(d["roofline_splat"]["frac"], 3), "gather kernel frac", round(d["roofline_splat"]["kernel_frac"], 3))
 except Exception as e:
     print("no bench line", e)
 PY

@@ -1,4 +1,4 @@
-"""DRAM traffic per launch of every kernel in an .ncu-rep -> profiles/r1_traffic.json (read by bench.py).
+"""DRAM traffic per launch of every kernel in an .ncu-rep -> profiles/r2_traffic.json (read by bench.py).
 
     python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep [more.ncu-rep ...]
 """
@@ -27,6 +27,6 @@ for rep in sys.argv[1:]:
         out.setdefault(name, []).append(b)
 res = {"source": [os.path.basename(r) for r in sys.argv[1:]], "metric": "dram__bytes_read.sum + dram__bytes_write.sum, per launch (mean over the captured launches)",
        "traffic_bytes_per_launch": {k: sum(v) / len(v) for k, v in out.items()}}
-with open(os.path.join(ROOT, "profiles", "r1_traffic.json"), "w") as f:
+with open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w") as f:
     json.dump(res, f, indent=1)
 print(json.dumps(res, indent=1))
