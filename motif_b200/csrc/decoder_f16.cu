@@ -959,6 +959,8 @@ __device__ __forceinline__ QEpi q_make_epi(QBars& bars, bool wait_v1) {
 // first-generation loop (twelve instructions per failed try) against 2.43 ms with the lean one, synth_q 1.01 against 0.99 ms --
 // how fast the waiting epilogue warps of a slot re-poll shifts the phase in which the four slots of an SM meet on the MUFU pipe.
 __device__ __forceinline__ void q_take_d(QEpi& c, uint32_t (&r)[64], bool release) {
+  // (every warp polls for itself: letting one warp of the slot poll and the other three block in a named barrier locks the four
+  //  warps -- four different SMSPs -- to the slowest of them at every hand-off: flow_bin_q 2.31 -> 3.17 ms, measured)
   if (c.wait_v1)
     mbar_wait_v1(&c.bars->d_ready[c.tile], c.ph_d);
   else
@@ -1391,11 +1393,11 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
   const float t = time_of(times, nl);
   const int qy = (blk / blocks_x) * kGH + warp;
   const int x0 = (blk % blocks_x) * kGW;
-  if (qy >= g.HH) return;  // whole warps only; no block-wide barrier below
+  const bool active = qy < g.HH;  // whole warps only
   const int n_dest = min(kGW, g.WW - x0);
-  const size_t d0 = ((size_t)nl * B + b) * qs + (size_t)qy * g.WW + x0;  // first destination of the warp
+  const size_t d0 = ((size_t)nl * B + b) * qs + (size_t)(active ? qy : 0) * g.WW + x0;  // first destination of the warp
   // ---- the 32 lists of the warp are contiguous (4 KB): asynchronous copy into shared memory ----
-  {
+  if (active) {
     const uint4* src = reinterpret_cast<const uint4*>(sc.bin_ent + d0 * kSlots);
     uint4* dst = reinterpret_cast<uint4*>(&ent_s[warp][0][0]);
 #pragma unroll
@@ -1405,11 +1407,12 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
       cp_async16(dst + idx, on ? src + idx : src, on);
     }
   }
-  // rank-1 input weights, pre-scaled by 30, in shared memory (read once per destination):
+  // rank-1 input weights, pre-scaled by 30, in shared memory (read once per destination), written once per CTA -- the first
+  // version let every warp write the same values without a barrier: a benign overlap that racecheck reports, and eight times the loads:
   // s_e0[ch] = (bias [in rtab], w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t, 0)
   //   ->  rk_s[group][.] = 24 floats: per channel of the group (w_dx, w_dy, w_zmax, w_cnt, w_wz, w_t t)
-  for (int idx = lane; idx < 16 * 6; idx += 32) {
-    const int grp = idx / 6, k = idx - grp * 6;
+  if (threadIdx.x < 16 * 6) {
+    const int grp = threadIdx.x / 6, k = threadIdx.x - grp * 6;
     float v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -1421,7 +1424,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
   }
   // ---- per-destination scalars (Ours.py:813-814, 826-829, 834), lane <-> destination; re-arm the accumulators ----
   // par_s[j] = (1/wz, dx', dy', zmax), (count/16, wz/count, nearest LR latent [int], list length [int, -1: outside])
-  {
+  if (active) {
     const bool live = lane < n_dest;
     const size_t d = d0 + (live ? lane : 0);
     float4 side = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1459,7 +1462,8 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
     par_s[warp][lane][1] = make_float4(__fdiv_rn(cnt, 16.0f), __fdiv_rn(wz_, cnt_), __int_as_float(qu.iy * g.W + qu.ix), __int_as_float(live ? cnt_i : -1));
   }
   cp_async_wait_all();
-  __syncwarp();
+  __syncthreads();  // rk_s is visible to every warp (the kernel's only block-wide barrier; also orders each warp's own lists and scalars)
+  if (!active) return;
 
   const float4* Y4 = reinterpret_cast<const float4*>(sc.Y) + l16;
   const float4* R4 = reinterpret_cast<const float4*>(sc.rtab + (size_t)b * P * 64) + l16;
