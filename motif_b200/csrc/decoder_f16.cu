@@ -1302,6 +1302,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_bin_q_kernel(motif_geom_t g,
         const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(fy == fy ? fy : 3.0e38f));
         if (lane == 0 && m != 0u) atomicMax(band.flow_y_max + (blockIdx.x & 63), m);
       }
+      // (an L2 prefetch of the scatter's target lines issued here, several thousand cycles before the deferred atomics, costs more
+      //  issue slots and registers than the DRAM round trips it saves: flow_bin_q 2.34 -> 2.45 ms, measured)
       p_dx = dx, p_dy = dy, p_z = zraw, p_item = item;
     }
     if (p_item >= 0) scatter(p_item, p_dx, p_dy, p_z);
@@ -1407,13 +1409,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
 #ifndef MOTIF_GATHER_NO_PF
   prefetch_block(blk, nl);
 #endif
-#if defined(MOTIF_GATHER_PF2) && MOTIF_GATHER_PF2 > 0
-  if ((int)blockIdx.x + MOTIF_GATHER_PF2 < (int)gridDim.x) {
-    int pb, pn;
-    locate((int)blockIdx.x + MOTIF_GATHER_PF2 + bid0, pb, pn);
-    prefetch_block(pb, pn);
-  }
-#endif
+  // (a guess prefetch of the per-source rows Y around the block, by the CTAs of a group's first timestamp: no gain, measured)
   const float t = time_of(times, nl);
   const int qy = (blk / blocks_x) * kGH + warp;
   const int x0 = (blk % blocks_x) * kGW;
