@@ -1392,28 +1392,19 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
     }
   };
   locate((int)blockIdx.x + bid0, blk, nl);
-  // L2 line prefetch of this CTA's own lists and accumulators, first thing in the kernel.  They come from HBM (flow_bin_q wrote
-  // them one kernel earlier) and the prologue below asks for them in 16-byte pieces (cp.async of the lists, one float4 / float /
-  // int per destination): requesting the whole 128-byte lines up front -- one instruction per warp for the 4 KB of its lists --
-  // took the kernel from 2.02 to 1.66 ms (measured; a prefetch distance of 1 .. 100 CTAs ahead gives the same, 222+ less).
-  auto prefetch_block = [&](int pb, int pn) {
-    const int py = (pb / blocks_x) * kGH + warp, px0 = (pb % blocks_x) * kGW;
-    if (py < g.HH) {
-      const size_t pd0 = ((size_t)pn * B + b) * qs + (size_t)py * g.WW + px0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(sc.bin_ent + pd0 * kSlots) + 128 * lane));  // 32 lists of 128 B
-      if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(sc.side + pd0 * 4) + 128 * lane));
-      if (lane == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.zmax + pd0));
-      if (lane == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.bin_count + pd0));
-    }
-  };
-#ifndef MOTIF_GATHER_NO_PF
-  prefetch_block(blk, nl);
-#endif
   // (a guess prefetch of the per-source rows Y around the block, by the CTAs of a group's first timestamp: no gain, measured)
   const float t = time_of(times, nl);
   const int qy = (blk / blocks_x) * kGH + warp;
   const int x0 = (blk % blocks_x) * kGW;
   const bool active = qy < g.HH;  // whole warps only
+#ifdef MOTIF_GATHER_LDST
+  if (qy < g.HH) {  // (A/B arm: the load + store re-arm with its accumulator lines prefetched into L2)
+    const size_t pd0 = ((size_t)nl * B + b) * qs + (size_t)qy * g.WW + x0;
+    if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(sc.side + pd0 * 4) + 128 * lane));
+    if (lane == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.zmax + pd0));
+    if (lane == 5) asm volatile("prefetch.global.L2 [%0];" ::"l"(sc.bin_count + pd0));
+  }
+#endif
   const int n_dest = min(kGW, g.WW - x0);
   const size_t d0 = ((size_t)nl * B + b) * qs + (size_t)(active ? qy : 0) * g.WW + x0;  // first destination of the warp
   // ---- the 32 lists of the warp are contiguous (4 KB): asynchronous copy into shared memory ----
@@ -1452,12 +1443,25 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
     int cnt_i = 0;
     if (live) {
       float4* side_p = reinterpret_cast<float4*>(sc.side + d * 4);
+      // Read and re-arm in ONE L2 operation per array (atom.exch).  The first version loaded the cell and then stored the armed
+      // value to the same address: a store behind an outstanding load miss to its own line (the cells come from HBM, flow_bin_q wrote
+      // them one kernel earlier) stalled the SM's L1 far beyond the miss itself -- 2.02 ms; with the lines prefetched into L2 at kernel
+      // entry 1.62 ms; with the exchange 1.57 ms, prefetch or not (ld.global.cg instead of the plain load: no help, 2.01 ms).
+#ifdef MOTIF_GATHER_LDST
       side = *side_p;
       zm = sc.zmax[d];
       cnt_i = sc.bin_count[d];
       *side_p = make_float4(0.f, 0.f, 0.f, 0.f);
       sc.zmax[d] = 1.0f;
       sc.bin_count[d] = 0;
+#else
+      asm volatile("{\n\t.reg .b128 o, z;\n\tmov.b128 z, {%5, %5, %5, %5};\n\tatom.global.exch.b128 o, [%4], z;\n\tmov.b128 {%0, %1, %2, %3}, o;\n\t}"
+                   : "=f"(side.x), "=f"(side.y), "=f"(side.z), "=f"(side.w)
+                   : "l"(side_p), "r"(0)
+                   : "memory");
+      zm = atomicExch(sc.zmax + d, 1.0f);
+      cnt_i = atomicExch(sc.bin_count + d, 0);
+#endif
     }
     const float wz = side.z == 0.0f ? 1.0f : side.z;
     const float cnt = (float)cnt_i;
