@@ -1372,7 +1372,7 @@ __global__ void __launch_bounds__(256, 3) gather_l0_kernel(motif_geom_t g, int B
 
   __shared__ uint2 ent_s[kGH][kGW][kSlots];  // the warp's 32 destination lists (4 KB per warp)
   __shared__ float4 par_s[kGH][kGW][2];      // per-destination scalars (1 KB per warp)
-  __shared__ float4 rk_s[16][7];             // rank-1 layer-0 weights per 4-channel group (every warp writes the same values)
+  __shared__ float4 rk_s[16][7];             // rank-1 layer-0 weights per 4-channel group (written once per CTA)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = lane >> 4, l16 = lane & 15;
   const int qs = g.HH * g.WW, P = g.H * g.W;
   const int blocks_x = (g.WW + kGW - 1) / kGW, blocks_y = (g.HH + kGH - 1) / kGH;
