@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kLookWarps * 32) raft_corr_lookup_kernel(const
 // 32 strided ones (the generic kernel above is bound by its 32 wavefronts per load), keeps the 64 partial dot products in
 // registers and finishes them with a transposing butterfly: 62 shuffles for all 64 sums instead of 5 per sum.
 template <int CV>  // CV = C / 128
-__global__ void __launch_bounds__(kLookWarps * 32) raft_corr_lookup64_kernel(const float* __restrict__ fmap1, const float* __restrict__ fmap2,
+__global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(const float* __restrict__ fmap1, const float* __restrict__ fmap2,
                                                                              const float* __restrict__ coords, float* __restrict__ out,
                                                                              int B, int H, int W, int H2, int W2, int r) {
   __shared__ float s_dot[kLookWarps][64];
@@ -97,37 +97,40 @@ __global__ void __launch_bounds__(kLookWarps * 32) raft_corr_lookup64_kernel(con
   const float tx = cx - fx, ty = cy - fy;
   const int x0 = (int)fx - r, y0 = (int)fy - r;
   const float* f2b = fmap2 + (long long)b * H2 * W2 * C + 4 * lane;
-  float part[64];
+  // Two passes of 32 neighbourhood positions each: 32 partial sums in registers instead of 64 lets three CTAs share an SM instead
+  // of two (the kernel is latency-bound: every position is an independent 512-byte row load), and the transposing butterfly of a
+  // pass (31 shuffles) leaves lane l with the finished sum of position 32 * pass + l.
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float part[32];
 #pragma unroll
-  for (int pos = 0; pos < 64; ++pos) {
-    const int i = pos >> 3, j = pos & 7;  // slot (i, j) of an 8 x 8 grid; only i, j < n are used
-    const int xx = x0 + i, yy = y0 + j;
-    float d = 0.0f;
-    if (i < n && j < n && xx >= 0 && xx < W2 && yy >= 0 && yy < H2) {
-      const float* row = f2b + ((long long)yy * W2 + xx) * C;
+    for (int p = 0; p < 32; ++p) {
+      const int pos = 32 * pass + p;
+      const int i = pos >> 3, j = pos & 7;  // slot (i, j) of an 8 x 8 grid; only i, j < n are used
+      const int xx = x0 + i, yy = y0 + j;
+      float d = 0.0f;
+      if (i < n && j < n && xx >= 0 && xx < W2 && yy >= 0 && yy < H2) {
+        const float* row = f2b + ((long long)yy * W2 + xx) * C;
 #pragma unroll
-      for (int v = 0; v < CV; ++v) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
-        d = fmaf(a[v].x, w.x, fmaf(a[v].y, w.y, fmaf(a[v].z, w.z, fmaf(a[v].w, w.w, d))));
+        for (int v = 0; v < CV; ++v) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
+          d = fmaf(a[v].x, w.x, fmaf(a[v].y, w.y, fmaf(a[v].z, w.z, fmaf(a[v].w, w.w, d))));
+        }
+      }
+      part[p] = d;
+    }
+    // transposing butterfly: after the step with offset o a lane keeps the half of its values selected by (lane & o)
+#pragma unroll
+    for (int half = 16, o = 16; half >= 1; half >>= 1, o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float send = up ? part[i] : part[i + half];
+        const float keep = up ? part[i + half] : part[i];
+        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
-    part[pos] = d;
-  }
-  // transposing butterfly: after the step with offset o a lane keeps the half of its values selected by (lane & o)
-#pragma unroll
-  for (int half = 32, o = 16; half >= 2; half >>= 1, o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = up ? part[i] : part[i + half];
-      const float keep = up ? part[i + half] : part[i];
-      part[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-  {
-    const int base = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
-    s_dot[warp][base] = part[0];
-    s_dot[warp][base + 1] = part[1];
+    s_dot[warp][32 * pass + lane] = part[0];
   }
   __syncwarp();
   const float w00 = (1.0f - tx) * (1.0f - ty), w10 = tx * (1.0f - ty), w01 = (1.0f - tx) * ty, w11 = tx * ty;
