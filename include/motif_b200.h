@@ -105,6 +105,12 @@ int motif_flow_front(const float* fr0, const float* fr1, const float* flow, cons
  * ---------------------------------------------------------------------------------- */
 int motif_raft_corr_lookup(const float* fmap1, const float* fmap2, const float* coords, float* out, int B, int H, int W, int H2,
                            int W2, int C, int r, void* stream);
+/* The whole AlternateCorrBlock.__call__ (models/core/corr.py:69-87) in one launch: fmap2_levels[l] [B, h2[l], w2[l], C] is fmap2
+ * average-pooled l times (corr.py:64-67), coords [B, H, W, 2] the level-0 coordinates (divided by 2^l per level as corr.py:80 does),
+ * out the stacked [B, n_levels * (2r+1)^2, H, W] tensor (corr.py:85-86), divided by sqrt(C) when normalize != 0 (corr.py:87).
+ * fmap2_levels / h2 / w2 are HOST arrays of n_levels <= 4 entries.  r <= 3, C = 128 or 256 (RAFT small / full). */
+int motif_raft_corr_lookup_pyramid(const float* fmap1, const float* const* fmap2_levels, const int* h2, const int* w2, int n_levels,
+                                   const float* coords, float* out, int B, int H, int W, int C, int r, int normalize, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Modulated deformable convolution (DCNv2) forward, 3x3 / stride 1 / padding 1 / dilation 1.  Replaces

@@ -30,6 +30,7 @@ EXPORTS = [
     "motif_corr_fwd",
     "motif_flow_front",
     "motif_raft_corr_lookup",
+    "motif_raft_corr_lookup_pyramid",
     "motif_dcn_v2_fwd",
     "motif_frame_metrics",
     "motif_query_geometry",
@@ -115,6 +116,9 @@ def _declare(lib):
     lib.motif_flow_front.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]
     lib.motif_raft_corr_lookup.restype = c_int
     lib.motif_raft_corr_lookup.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    lib.motif_raft_corr_lookup_pyramid.restype = c_int
+    lib.motif_raft_corr_lookup_pyramid.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_void_p, c_void_p,
+                                                   c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
     lib.motif_dcn_v2_fwd.restype = c_int
     lib.motif_dcn_v2_fwd.argtypes = [c_void_p] * 6 + [c_int] * 6 + [c_void_p]
     lib.motif_frame_metrics.restype = c_int

@@ -74,13 +74,27 @@ __global__ void __launch_bounds__(kLookWarps * 32) raft_corr_lookup_kernel(const
 // (x C / 128), so the warp reads each 512-byte feature row of the neighbourhood with ONE coalesced LDG.128 instead of
 // 32 strided ones (the generic kernel above is bound by its 32 wavefronts per load), keeps the 64 partial dot products in
 // registers and finishes them with a transposing butterfly: 62 shuffles for all 64 sums instead of 5 per sum.
+// blockIdx.y = pyramid level: the whole AlternateCorrBlock.__call__ (corr.py:69-87) in one launch -- level l samples fmap2 pooled
+// l times at coords / 2^l and writes channels [l (2r+1)^2, (l+1) (2r+1)^2) of the stacked output; with `inv_norm` the result is
+// divided by sqrt(C) as corr.py:87 does.  The one-level entry point passes a single level, scale 1 and no normalisation.
+struct LookupLevels {
+  const float* fmap2[4];
+  int h2[4], w2[4];
+  int n_levels;
+  float norm;  // 0: none; else 1 / sqrt(C) (torch divides a CUDA tensor by a CPU scalar tensor as a * (1 / b), BinaryDivTrueKernel.cu)
+};
 template <int CV>  // CV = C / 128
-__global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(const float* __restrict__ fmap1, const float* __restrict__ fmap2,
+__global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(const float* __restrict__ fmap1, LookupLevels lv,
                                                                              const float* __restrict__ coords, float* __restrict__ out,
-                                                                             int B, int H, int W, int H2, int W2, int r) {
+                                                                             int B, int H, int W, int r) {
   __shared__ float s_dot[kLookWarps][64];
   constexpr int C = 128 * CV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int level = blockIdx.y;
+  const float* __restrict__ fmap2 = level == 0 ? lv.fmap2[0] : level == 1 ? lv.fmap2[1] : level == 2 ? lv.fmap2[2] : lv.fmap2[3];
+  const int H2 = level == 0 ? lv.h2[0] : level == 1 ? lv.h2[1] : level == 2 ? lv.h2[2] : lv.h2[3];
+  const int W2 = level == 0 ? lv.w2[0] : level == 1 ? lv.w2[1] : level == 2 ? lv.w2[2] : lv.w2[3];
+  const float cscale = 1.0f / (float)(1 << level);  // coords / 2**level (corr.py:80): exact
   const long long q = (long long)blockIdx.x * kLookWarps + warp;
   const long long hw = (long long)H * W;
   if (q >= (long long)B * hw) return;
@@ -89,7 +103,7 @@ __global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(
   float4 a[CV];
 #pragma unroll
   for (int v = 0; v < CV; ++v) a[v] = __ldg(reinterpret_cast<const float4*>(fmap1 + q * C + 128 * v) + lane);
-  float cx = __ldg(coords + 2 * q), cy = __ldg(coords + 2 * q + 1);
+  float cx = __ldg(coords + 2 * q) * cscale, cy = __ldg(coords + 2 * q + 1) * cscale;
   const bool finite = isfinite(cx) && isfinite(cy);
   cx = finite ? fminf(fmaxf(cx, -1.0e6f), 1.0e6f) : -1.0e6f;
   cy = finite ? fminf(fmaxf(cy, -1.0e6f), 1.0e6f) : -1.0e6f;
@@ -97,25 +111,31 @@ __global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(
   const float tx = cx - fx, ty = cy - fy;
   const int x0 = (int)fx - r, y0 = (int)fy - r;
   const float* f2b = fmap2 + (long long)b * H2 * W2 * C + 4 * lane;
-  // Two passes of 32 neighbourhood positions each: 32 partial sums in registers instead of 64 lets three CTAs share an SM instead
-  // of two (the kernel is latency-bound: every position is an independent 512-byte row load), and the transposing butterfly of a
-  // pass (31 shuffles) leaves lane l with the finished sum of position 32 * pass + l.
+  // The kernel issued ~1800 instructions per query, most of them per-position bounds tests and address arithmetic: validity of the
+  // 8 x 8 slots is now two bit masks, the address one row offset (per slot row j) plus one column offset (per slot column i), both
+  // clamped into the map so that every load is legal, and the sum of a slot outside the map is zeroed by one select afterwards.
+  unsigned vx = 0u, vy = 0u;
+  int coff[8], roff[8];  // element offsets inside this batch item's map (H2 * W2 * C < 2^31, checked by the launcher)
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int xx = x0 + t, yy = y0 + t;
+    vx |= (t < n && xx >= 0 && xx < W2) ? (1u << t) : 0u;
+    vy |= (t < n && yy >= 0 && yy < H2) ? (1u << t) : 0u;
+    coff[t] = min(max(xx, 0), W2 - 1) * C;
+    roff[t] = min(max(yy, 0), H2 - 1) * W2 * C;
+  }
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     float part[32];
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
-      const int pos = 32 * pass + p;
-      const int i = pos >> 3, j = pos & 7;  // slot (i, j) of an 8 x 8 grid; only i, j < n are used
-      const int xx = x0 + i, yy = y0 + j;
+      // slot (i, j) = (4 * pass + (p >> 3), p & 7) of the 8 x 8 grid (position 32 * pass + p)
+      const float* row = f2b + (roff[p & 7] + (pass == 0 ? coff[p >> 3] : coff[4 + (p >> 3)]));
       float d = 0.0f;
-      if (i < n && j < n && xx >= 0 && xx < W2 && yy >= 0 && yy < H2) {
-        const float* row = f2b + ((long long)yy * W2 + xx) * C;
 #pragma unroll
-        for (int v = 0; v < CV; ++v) {
-          const float4 w = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
-          d = fmaf(a[v].x, w.x, fmaf(a[v].y, w.y, fmaf(a[v].z, w.z, fmaf(a[v].w, w.w, d))));
-        }
+      for (int v = 0; v < CV; ++v) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + 128 * v));
+        d = fmaf(a[v].x, w.x, fmaf(a[v].y, w.y, fmaf(a[v].z, w.z, fmaf(a[v].w, w.w, d))));
       }
       part[p] = d;
     }
@@ -130,7 +150,10 @@ __global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(
         part[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
-    s_dot[warp][32 * pass + lane] = part[0];
+    {  // lane l holds position 32 * pass + l = slot (4 * pass + (l >> 3), l & 7)
+      const bool ok = ((vx >> (4 * pass + (lane >> 3))) & (vy >> (lane & 7)) & 1u) != 0u;
+      s_dot[warp][32 * pass + lane] = ok ? part[0] : 0.0f;
+    }
   }
   __syncwarp();
   const float w00 = (1.0f - tx) * (1.0f - ty), w10 = tx * (1.0f - ty), w01 = (1.0f - tx) * ty, w11 = tx * ty;
@@ -138,8 +161,9 @@ __global__ void __launch_bounds__(kLookWarps * 32, 3) raft_corr_lookup64_kernel(
   for (int o = lane; o < nw * nw; o += 32) {
     const int ai = o / nw, c = o - ai * nw;
     const float* d = &s_dot[warp][ai * 8 + c];
-    const float v = w00 * d[0] + w10 * d[8] + w01 * d[1] + w11 * d[9];
-    out[(((long long)b * nw * nw + o) * H + y) * W + x] = finite ? v : 0.0f;
+    float v = w00 * d[0] + w10 * d[8] + w01 * d[1] + w11 * d[9];
+    if (lv.norm != 0.0f) v = __fmul_rn(v, lv.norm);
+    out[(((long long)b * lv.n_levels * nw * nw + (long long)level * nw * nw + o) * H + y) * W + x] = finite ? v : 0.0f;
   }
 }
 
@@ -156,16 +180,49 @@ extern "C" int motif_raft_corr_lookup(const float* fmap1, const float* fmap2, co
   MOTIF_REQUIRE((C & 3) != 0 || ((((uintptr_t)fmap1 | (uintptr_t)fmap2) & 15) == 0), "raft_corr_lookup: feature maps must be 16-byte aligned");
   const long long queries = (long long)B * H * W;
   MOTIF_REQUIRE(queries < (1LL << 31), "raft_corr_lookup: too many queries");
+  MOTIF_REQUIRE((long long)H2 * W2 * C < (1LL << 31), "raft_corr_lookup: feature map too large");
   ProfScope prof("raft_corr_lookup_kernel", (cudaStream_t)stream);
   static const bool generic_only = getenv("MOTIF_RAFT_GENERIC") != nullptr;
   if (!generic_only && r <= 3 && (C == 128 || C == 256) && ((((uintptr_t)fmap1 | (uintptr_t)fmap2) & 15) == 0)) {
     const int grid = ceil_div(queries, kLookWarps);
-    if (C == 128) raft_corr_lookup64_kernel<1><<<grid, kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, B, H, W, H2, W2, r);
-    else raft_corr_lookup64_kernel<2><<<grid, kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, B, H, W, H2, W2, r);
+    LookupLevels lv{};
+    lv.fmap2[0] = fmap2, lv.h2[0] = H2, lv.w2[0] = W2, lv.n_levels = 1, lv.norm = 0.0f;
+    if (C == 128) raft_corr_lookup64_kernel<1><<<grid, kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, lv, coords, out, B, H, W, r);
+    else raft_corr_lookup64_kernel<2><<<grid, kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, lv, coords, out, B, H, W, r);
     MOTIF_LAUNCHED("raft_corr_lookup_kernel");
     return 0;
   }
   raft_corr_lookup_kernel<<<ceil_div(queries, kLookWarps), kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, fmap2, coords, out, B, H, W, H2, W2, C, r);
+  MOTIF_LAUNCHED("raft_corr_lookup_kernel");
+  return 0;
+}
+
+// All pyramid levels of AlternateCorrBlock.__call__ (models/core/corr.py:69-87) in ONE launch: fmap2_levels[l] is fmap2 pooled l times
+// ([B, h2[l], w2[l], C] channels-last), coords [B, H, W, 2] are the level-0 coordinates (the kernel divides by 2^l), out is the stacked
+// [B, n_levels * (2r+1)^2, H, W] tensor, already divided by sqrt(C) when `normalize` is set (corr.py:87).  r <= 3, C = 128 or 256.
+extern "C" int motif_raft_corr_lookup_pyramid(const float* fmap1, const float* const* fmap2_levels, const int* h2, const int* w2, int n_levels,
+                                              const float* coords, float* out, int B, int H, int W, int C, int r, int normalize, void* stream) {
+  MOTIF_REQUIRE(fmap1 && fmap2_levels && h2 && w2 && coords && out, "raft_corr_lookup_pyramid: null pointer");
+  MOTIF_REQUIRE(n_levels >= 1 && n_levels <= 4, "raft_corr_lookup_pyramid: %d levels outside [1, 4]", n_levels);
+  MOTIF_REQUIRE(B > 0 && H > 0 && W > 0, "raft_corr_lookup_pyramid: non-positive size");
+  MOTIF_REQUIRE(r >= 0 && r <= 3 && (C == 128 || C == 256), "raft_corr_lookup_pyramid: r=%d, C=%d (supported: r <= 3, C = 128 / 256)", r, C);
+  const long long queries = (long long)B * H * W;
+  MOTIF_REQUIRE(queries < (1LL << 31), "raft_corr_lookup_pyramid: too many queries");
+  LookupLevels lv{};
+  uintptr_t align = (uintptr_t)fmap1;
+  for (int l = 0; l < n_levels; ++l) {
+    MOTIF_REQUIRE(fmap2_levels[l] != nullptr && h2[l] > 0 && w2[l] > 0, "raft_corr_lookup_pyramid: level %d is empty", l);
+    MOTIF_REQUIRE((long long)h2[l] * w2[l] * C < (1LL << 31), "raft_corr_lookup_pyramid: feature map too large");
+    lv.fmap2[l] = fmap2_levels[l], lv.h2[l] = h2[l], lv.w2[l] = w2[l];
+    align |= (uintptr_t)fmap2_levels[l];
+  }
+  MOTIF_REQUIRE((align & 15) == 0, "raft_corr_lookup_pyramid: feature maps must be 16-byte aligned");
+  lv.n_levels = n_levels;
+  lv.norm = normalize ? 1.0f / sqrtf((float)C) : 0.0f;
+  ProfScope prof("raft_corr_lookup_kernel", (cudaStream_t)stream);
+  dim3 grid(ceil_div(queries, kLookWarps), n_levels);
+  if (C == 128) raft_corr_lookup64_kernel<1><<<grid, kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, lv, coords, out, B, H, W, r);
+  else raft_corr_lookup64_kernel<2><<<grid, kLookWarps * 32, 0, (cudaStream_t)stream>>>(fmap1, lv, coords, out, B, H, W, r);
   MOTIF_LAUNCHED("raft_corr_lookup_kernel");
   return 0;
 }

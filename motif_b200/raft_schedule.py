@@ -43,6 +43,9 @@ class LookupBlock:
     def __call__(self, coords):
         coords = coords.permute(0, 2, 3, 1)
         B, H, W, _ = coords.shape
+        if self.f1.is_cuda and self.dim in (128, 256) and self.radius <= 3 and self.num_levels <= 4:
+            # one launch for all levels: coords / 2^l, the stacking and the division by sqrt(dim) happen inside the kernel
+            return alt_cuda_corr.forward_pyramid(self.f1, self.f2, coords.float(), self.radius, normalize=True)
         out = []
         for i in range(self.num_levels):
             coords_i = (coords / 2 ** i).reshape(B, 1, H, W, 2).contiguous()

@@ -89,6 +89,31 @@ def test_install_rebinds_the_reference_import():
         sys.modules.pop("alt_cuda_corr", None)
 
 
+@pytest.mark.parametrize("C,levels", [(128, 4), (256, 3), (128, 1)])
+def test_pyramid_lookup_is_bit_equal_to_the_level_by_level_path(C, levels):
+    """``motif_raft_corr_lookup_pyramid`` (every level of AlternateCorrBlock.__call__ in one launch: coords / 2^l, the stacking and
+    the division by sqrt(C) inside the kernel) against the same block assembled from per-level ``alt_cuda_corr.forward`` calls and
+    torch ops as corr.py:69-87 writes it; also with coordinates far outside the map and non-finite ones."""
+    from motif_b200 import alt_cuda_corr
+
+    g = torch.Generator().manual_seed(C + levels)
+    B, H, W = 2, 20, 28
+    f1, f2 = torch.randn(B, C, H, W, generator=g).cuda(), torch.randn(B, C, H, W, generator=g).cuda()
+    ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    coords = torch.stack([xs, ys])[None].repeat(B, 1, 1, 1) + torch.randn(B, 2, H, W, generator=g) * 6.0
+    coords[0, :, 0, 0] = torch.tensor([1.0e7, -3.0])
+    coords[1, :, 3, 5] = torch.tensor([float("nan"), 2.0])
+    coords = coords.cuda()
+    want = _alternate_block(f1, f2, coords, levels, 3)
+    pyr = [f2]
+    for _ in range(levels - 1):
+        pyr.append(F.avg_pool2d(pyr[-1], 2, stride=2))
+    got = alt_cuda_corr.forward_pyramid(f1.permute(0, 2, 3, 1).contiguous(), [p.permute(0, 2, 3, 1).contiguous() for p in pyr],
+                                        coords.permute(0, 2, 3, 1).contiguous(), 3, normalize=True)
+    assert got.shape == want.shape == (B, levels * 49, H, W)
+    assert torch.equal(got, want)
+
+
 def test_lookup_block_equals_the_oracle_block():
     """``raft_schedule.LookupBlock`` (AlternateCorrBlock with the layout changes hoisted out of the iteration loop) against the
     oracle's restatement of ``CorrBlock`` (pinned by the reference's own class, tests/golden/raft_corr.npz); called twice with

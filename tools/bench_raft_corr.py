@@ -53,6 +53,10 @@ def lookup_new():
     return torch.stack(out, 1).reshape(B, -1, H, W) / C ** 0.5
 
 
+def lookup_pyramid():
+    return alt_cuda_corr.forward_pyramid(f1n, f2n, coords.permute(0, 2, 3, 1).contiguous(), r, normalize=True)
+
+
 def timed(fn, reps=20):
     for _ in range(3):
         fn()
@@ -74,6 +78,9 @@ for _ in range(10):
     lookup_new()
 p = _lib.prof_collect(["raft_corr_lookup_kernel"])["raft_corr_lookup_kernel"]
 _lib.prof_enable(False)
+t_pyr = timed(lookup_pyramid)
+print("one-launch pyramid lookup (motif_raft_corr_lookup_pyramid): %.3f ms per RAFT iteration, bit-equal to the level-by-level path: %s"
+      % (t_pyr, bool(torch.equal(lookup_pyramid(), lookup_new()))))
 flops = sum(2 * (2 * r + 2) ** 2 * C * B * H * W for _ in range(L))
 print("lookup, one RAFT iteration (4 levels, 90x160, C=128, r=3): this repo %.3f ms (kernels %.3f ms, %.2f TFLOP/s fp32), CorrBlock lookup %.3f ms + "
       "%.2f ms once per pair to build its %.0f MB volume pyramid; 12 iterations: %.2f ms vs %.2f ms"
