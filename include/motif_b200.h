@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MOTIF_ABI_VERSION 4
+#define MOTIF_ABI_VERSION 5
 
 #define MOTIF_E_BADARG (-1)   /* null pointer, non-positive size, unknown mode        */
 #define MOTIF_E_WORKSPACE (-2) /* workspace smaller than the *_workspace_bytes() answer */
@@ -204,6 +204,8 @@ typedef struct {
   int weights_ready;   /* 1: `workspace` still holds the weight images a previous motif_decode wrote for THESE weights at THIS
                         * precision (same workspace pointer, nothing else wrote to it): the per-call repacking is skipped.
                         * Honoured by MOTIF_PRECISION_F16X3; 0 is always safe.                                          */
+  int latents_nchw;    /* 1: feat / flow_feat / residual are the reference's own NCHW tensors [R, 64, H, W] (no motif_pack_latents
+                        * pass): MOTIF_PRECISION_F16X3 only, whose per-LR-pixel tables are the only readers of the latents.     */
 } motif_decode_t;
 
 /* MLP arithmetic.  F16X3 (default of the Python mirror): tcgen05 kind::f16, every fp32 operand split into two

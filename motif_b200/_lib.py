@@ -85,6 +85,7 @@ class DecodeT(Structure):
         ("row_begin", c_int), ("row_end", c_int), ("halo", c_int),
         ("flow_y_max", c_void_p),
         ("weights_ready", c_int),
+        ("latents_nchw", c_int),
     ]
 
 

@@ -81,6 +81,8 @@ extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
   if (int rc = check_decode(args)) return rc;
   if (args->local_ensemble != 0 && args->precision == MOTIF_PRECISION_TF32X3)
     return fail(MOTIF_E_UNSUPPORTED, "decode: local_ensemble is implemented by MOTIF_PRECISION_F16X3 and MOTIF_PRECISION_FP32 (precision %d given)", args->precision);
+  if (args->latents_nchw != 0 && args->precision != MOTIF_PRECISION_F16X3)
+    return fail(MOTIF_E_UNSUPPORTED, "decode: NCHW latents are read by MOTIF_PRECISION_F16X3 only (precision %d given): pack them with motif_pack_latents", args->precision);
   if (args->row_end != 0 && args->precision != MOTIF_PRECISION_F16X3)
     return fail(MOTIF_E_UNSUPPORTED, "decode: destination row bands are implemented by MOTIF_PRECISION_F16X3 only (precision %d given)", args->precision);
   switch (args->precision) {

@@ -260,7 +260,11 @@ struct LrJobs {
 };
 // Two LR pixels per thread: every (broadcast) shared-memory load of a weight quad feeds eight FMAs instead of four -- the
 // kernel is bound by the LSU data pipe (a broadcast LDS.128 still writes 512 B back to the register file), not by FP32.
-__global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float* __restrict__ wp, int p_begin, int P) {
+// kNchw: x is the reference's own NCHW plane stack [64][P_img] of one image (element (k, p) at k * P_img + p: a warp's 32 pixels
+// read 128 contiguous bytes per channel) instead of the pixel-major copy -- the motif_pack_latents pass and its 73.7 MB round trip
+// per Adobe clip are then not needed at all (motif_decode_t.latents_nchw).
+template <bool kNchw>
+__global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float* __restrict__ wp, int p_begin, int P, int P_img) {
   __shared__ float4 w4[64 * 16];
   __shared__ float bias[64];
   const LrJob jb = jobs.j[blockIdx.y];
@@ -271,13 +275,20 @@ __global__ void __launch_bounds__(128) lr_tables_kernel(LrJobs jobs, const float
   if (p0 >= P) return;
   const bool two = p1 < P;
   float x0[64], x1[64];
-  const float4* xr0 = reinterpret_cast<const float4*>(jb.x + (size_t)p0 * 64);
-  const float4* xr1 = reinterpret_cast<const float4*>(jb.x + (size_t)(two ? p1 : p0) * 64);
+  if (kNchw) {
+    const float* c0 = jb.x + p0;
+    const float* c1 = jb.x + (two ? p1 : p0);
 #pragma unroll
-  for (int k4 = 0; k4 < 16; ++k4) {
-    const float4 v = __ldg(xr0 + k4), u = __ldg(xr1 + k4);
-    x0[4 * k4] = v.x, x0[4 * k4 + 1] = v.y, x0[4 * k4 + 2] = v.z, x0[4 * k4 + 3] = v.w;
-    x1[4 * k4] = u.x, x1[4 * k4 + 1] = u.y, x1[4 * k4 + 2] = u.z, x1[4 * k4 + 3] = u.w;
+    for (int k = 0; k < 64; ++k) x0[k] = __ldg(c0 + (size_t)k * P_img), x1[k] = __ldg(c1 + (size_t)k * P_img);
+  } else {
+    const float4* xr0 = reinterpret_cast<const float4*>(jb.x + (size_t)p0 * 64);
+    const float4* xr1 = reinterpret_cast<const float4*>(jb.x + (size_t)(two ? p1 : p0) * 64);
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+      const float4 v = __ldg(xr0 + k4), u = __ldg(xr1 + k4);
+      x0[4 * k4] = v.x, x0[4 * k4 + 1] = v.y, x0[4 * k4 + 2] = v.z, x0[4 * k4 + 3] = v.w;
+      x1[4 * k4] = u.x, x1[4 * k4 + 1] = u.y, x1[4 * k4 + 2] = u.z, x1[4 * k4 + 3] = u.w;
+    }
   }
   float4* o0 = reinterpret_cast<float4*>(jb.out + (size_t)p0 * 64);
   float4* o1 = reinterpret_cast<float4*>(jb.out + (size_t)(two ? p1 : p0) * 64);
@@ -1738,15 +1749,19 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st, 
     }
   }
 #endif
-  // LR tables
+  // LR tables (the latents are the same [R][P][64] / [R][64][P] blocks either way: image rb starts at rb * P * 64)
   LrJobs lj;
   int nj = 0;
+  auto launch_tables = [&](int n) {
+    if (a->latents_nchw) lr_tables_kernel<true><<<dim3(ceil_div(p_end - p_begin, 256), n), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end, P);
+    else lr_tables_kernel<false><<<dim3(ceil_div(p_end - p_begin, 256), n), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end, P);
+  };
   for (int rb = 0; rb < 2 * B; ++rb) {
     lj.j[nj++] = LrJob{a->flow_feat + (size_t)rb * P * 64, sc.p0f + (size_t)rb * P * 64, Wp::f_a0, -1, 0};
     lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.p0i + (size_t)rb * P * 64, Wp::i_a0, -1, 0};
     lj.j[nj++] = LrJob{a->feat + (size_t)rb * P * 64, sc.ftab + (size_t)rb * P * 64, Wp::s_a0b, -1, 0};
     if (nj + 4 > 16) {
-      lr_tables_kernel<<<dim3(ceil_div(p_end - p_begin, 256), nj), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end);
+      launch_tables(nj);
       MOTIF_LAUNCHED("lr_tables_kernel");
       nj = 0;
     }
@@ -1754,13 +1769,13 @@ static int prepare(const motif_decode_t* a, const Scratch& sc, cudaStream_t st, 
   for (int b = 0; b < B; ++b) {
     lj.j[nj++] = LrJob{a->residual + (size_t)b * P * 64, sc.rtab + (size_t)b * P * 64, Wp::s_a0c, Wp::s_e0, 8};
     if (nj == 16) {
-      lr_tables_kernel<<<dim3(ceil_div(p_end - p_begin, 256), nj), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end);
+      launch_tables(nj);
       MOTIF_LAUNCHED("lr_tables_kernel");
       nj = 0;
     }
   }
   if (nj > 0) {
-    lr_tables_kernel<<<dim3(ceil_div(p_end - p_begin, 256), nj), 128, 0, st>>>(lj, sc.wpack, p_begin, p_end);
+    launch_tables(nj);
     MOTIF_LAUNCHED("lr_tables_kernel");
   }
   return 0;

@@ -207,10 +207,16 @@ class SpaceTimeDecoder:
         n0, n1 = (0, N) if n_range is None else n_range
         dev = self.device
         with torch.cuda.device(dev):
-            lr_rows = None if row_range is None else self.lr_rows_of_band(H, HH, row_range, halo)
-            featp = self.pack_latents(feat, lr_rows)
-            ffp = self.pack_latents(flow_feat, lr_rows)
-            resp = self.pack_latents(residual, lr_rows)
+            # f16x3 reads the reference's NCHW tensors as they are (its per-LR-pixel tables are the only readers of the latents);
+            # the fp32 / tf32x3 kernels gather pixel-major rows and need the transposed copy
+            nchw = (precision or self.precision) == "f16x3"
+            if nchw:
+                featp, ffp, resp = feat.contiguous(), flow_feat.contiguous(), residual.contiguous()
+            else:
+                lr_rows = None if row_range is None else self.lr_rows_of_band(H, HH, row_range, halo)
+                featp = self.pack_latents(feat, lr_rows)
+                ffp = self.pack_latents(flow_feat, lr_rows)
+                resp = self.pack_latents(residual, lr_rows)
             if out is not None:
                 if out.shape != (N, B, 3, HH, WW) or out.dtype != torch.float32 or out.device != residual.device or not out.is_contiguous():
                     raise ValueError(f"out must be a contiguous fp32 [{N},{B},3,{HH},{WW}] tensor on {dev}")
@@ -237,6 +243,7 @@ class SpaceTimeDecoder:
             a.n_begin, a.n_end = int(n0), int(n1)
             a.precision = PRECISIONS[precision or self.precision]
             a.local_ensemble = int(self.local_ensemble)
+            a.latents_nchw = int(nchw)
             if row_range is not None:
                 a.row_begin, a.row_end, a.halo = int(row_range[0]), int(row_range[1]), int(halo)
                 if flow_y_max is not None:

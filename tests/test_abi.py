@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_launch_counter(lib):
-    assert lib.motif_abi_version() == 4
+    assert lib.motif_abi_version() == 5
     lib.motif_reset_launch_count()
     assert lib.motif_launch_count() == 0
 
