@@ -1911,8 +1911,12 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
       }
       {
         ProfScope prof("gather_l0_kernel", st);
-        static const int band_rows_env = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : kBandBlockRows;
-        const int band_rows = a->row_end > 0 ? kBandBlockRowsSharded : band_rows_env;  // tuning hook for the whole-image order only
+        // L2 band height: the per-source rows of a band (both reference frames, 32 rows x WW x 256 B x 2 per block row of 4) must
+        // stay in L2 while the band's timestamps run -- four block rows at 1280 columns, fewer for wider frames (4K, 3840 columns:
+        // gather 16.7 ms with four, 15.1 with two, 14.9 with one)
+        static const int band_rows_env = getenv("MOTIF_GATHER_BAND") ? atoi(getenv("MOTIF_GATHER_BAND")) : 0;  // tuning hook
+        const int by_width = 5120 / g.WW < 1 ? 1 : (5120 / g.WW > kBandBlockRows ? kBandBlockRows : 5120 / g.WW);
+        const int band_rows = a->row_end > 0 ? (by_width < kBandBlockRowsSharded ? by_width : kBandBlockRowsSharded) : (band_rows_env > 0 ? band_rows_env : by_width);
         static const int dsmem = getenv("MOTIF_GATHER_DSMEM") ? atoi(getenv("MOTIF_GATHER_DSMEM")) : 0;
         // band mode: the band's blocks are the CTAs [bid0, bid0 + nt * band_blocks) of the whole image's band-major order
         const int bid0 = (by0 / band_rows) * nt * band_rows * blocks_x;
