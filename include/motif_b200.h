@@ -118,6 +118,8 @@ int motif_raft_corr_lookup_pyramid(const float* fmap1, const float* const* fmap2
  * 125-195 + the SGEMM of src/cuda/dcn_v2_cuda.cu), which cannot be built on torch 2.x (THC).
  *   in [B, Cin, H, W]   offset [B, dg*18, H, W] (per group and tap: dh, dw)   mask [B, dg*9, H, W]
  *   weight [Cout, Cin, 3, 3]   bias [Cout] or NULL   out [B, Cout, H, W];   Cin / dg <= 8
+ * The model's configuration (Cin = Cout = 64, dg = 8: every call site of Ours.py:53-172) runs as an implicit GEMM on tcgen05 with
+ * fp32-equivalent two-piece fp16 operands (csrc/dcn_v2_tc.cu); every other shape on CUDA cores (csrc/dcn_v2.cu).
  * ---------------------------------------------------------------------------------- */
 int motif_dcn_v2_fwd(const float* in, const float* offset, const float* mask, const float* weight, const float* bias, float* out,
                      int B, int Cin, int Cout, int H, int W, int deformable_groups, void* stream);
