@@ -782,17 +782,21 @@ __global__ void __launch_bounds__(kThreads, 1) imnet_f16_kernel(motif_geom_t g, 
 #pragma unroll 1
       for (int ch = 0; ch < 4; ++ch) sine_epilogue(c, 0, s2, sm.consts + 320 + 64 * ch, kColA2, &sm.bars.a2_ready[c.tile], true);
       // output: Y = s3 * D1 + 30 * bias' + 30 * W0b * feat[nearest]
+      // (the nearest-feature table row is requested BEFORE the wait for the last accumulator, not behind it)
+      const float4* f4 = reinterpret_cast<const float4*>(sc.ftab + lr * 64 + 32 * c.half);
+      float4 fpre[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) fpre[j4] = __ldg(f4 + j4);
       wait_d(c, 1);
       {
         uint32_t r[32];
         ld_half(c, 1, r);
         release_d(c, 1);
-        const float4* f4 = reinterpret_cast<const float4*>(sc.ftab + lr * 64 + 32 * c.half);
         float4* dst = reinterpret_cast<float4*>(sc.Y + ((size_t)rb * qs + qc) * 64 + 32 * c.half);
         if (live) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 f = __ldg(f4 + j4);
+            const float4 f = fpre[j4];
             const float4 bb = *reinterpret_cast<const float4*>(sm.consts + 576 + 32 * c.half + 4 * j4);
             float4 v = make_float4(fmaf(__uint_as_float(r[4 * j4 + 0]), s3, bb.x) + f.x, fmaf(__uint_as_float(r[4 * j4 + 1]), s3, bb.y) + f.y,
                                    fmaf(__uint_as_float(r[4 * j4 + 2]), s3, bb.z) + f.z, fmaf(__uint_as_float(r[4 * j4 + 3]), s3, bb.w) + f.w);
