@@ -1855,7 +1855,8 @@ int decode_f16(const motif_decode_t* a, cudaStream_t st) {
   magic.w[0] = 0x4d6f5449u, magic.w[1] = ((uint32_t)g.B << 16) ^ (uint32_t)NT ^ 0x9e3779b9u;
   magic.w[2] = ((uint32_t)g.HH << 16) ^ (uint32_t)g.H ^ 0x85ebca6bu, magic.w[3] = ((uint32_t)g.WW << 16) ^ (uint32_t)g.W ^ 0xc2b2ae35u;
   none.w[0] = none.w[1] = none.w[2] = none.w[3] = 0u;
-  arm_kernel<<<n_sm * 8, 256, 0, st>>>(sc.armed, magic, reinterpret_cast<uint4*>(sc.side), sc.zero_bytes / 16, sc.zmax, (size_t)NT * g.B * qs);
+  // (one CTA of 1024 threads per SM: the common case is the early return, and 1184 small CTAs took 0.03 ms to come and go)
+  arm_kernel<<<n_sm, 1024, 0, st>>>(sc.armed, magic, reinterpret_cast<uint4*>(sc.side), sc.zero_bytes / 16, sc.zmax, (size_t)NT * g.B * qs);
   MOTIF_LAUNCHED("arm_kernel");
   mark_kernel<<<1, 32, 0, st>>>(sc.armed, none);
   MOTIF_LAUNCHED("mark_kernel");
