@@ -209,7 +209,7 @@ class SpaceTimeDecoder:
         with torch.cuda.device(dev):
             # f16x3 reads the reference's NCHW tensors as they are (its per-LR-pixel tables are the only readers of the latents);
             # the fp32 / tf32x3 kernels gather pixel-major rows and need the transposed copy
-            nchw = (precision or self.precision) == "f16x3"
+            nchw = (precision or self.precision) == "f16x3" and not getattr(self, "force_packed_latents", False)  # (test hook: the packed form of the C ABI)
             if nchw:
                 featp, ffp, resp = feat.contiguous(), flow_feat.contiguous(), residual.contiguous()
             else:

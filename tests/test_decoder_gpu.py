@@ -344,6 +344,30 @@ def test_f16x3_timestamp_groups_and_rearmed_workspace():
     assert (part[6:10] - rgb1[6:10]).abs().max().item() < 1e-5
 
 
+def test_nchw_latents_equal_the_packed_form():
+    """f16x3 reads the reference's NCHW latents directly (motif_decode_t.latents_nchw); the pixel-major form the C ABI also accepts
+    (motif_pack_latents) must give the same flows bit for bit and the same frames -- the per-LR-pixel tables see the same numbers in the
+    same order -- for the whole frame and for a destination row band (only the band's LR rows are tabulated)."""
+    from motif_b200 import synthetic
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
+    lat = [t.cuda() for t in synthetic.synthetic_latents(1, 24, 40, seed=3)]
+    tt = torch.tensor([[0.25, 0.5, 0.75]])
+    a = SpaceTimeDecoder(params, device="cuda", precision="f16x3")
+    b = SpaceTimeDecoder(params, device="cuda", precision="f16x3")
+    b.force_packed_latents = True
+    for kw in ({}, {"row_range": (32, 64), "halo": 16}):
+        ra, fa = a.decode(*lat, tt, (96, 160), **kw)
+        rb, fb = b.decode(*lat, tt, (96, 160), **kw)
+        rows = slice(*kw["row_range"]) if kw else slice(None)
+        # the flows have no atomics on their way: bit-equal; the frames sum list entries in the order the binning atomics handed the
+        # slots out, which differs from run to run in the last bits
+        assert (ra[..., rows, :] - rb[..., rows, :]).abs().max().item() < 1e-5
+        if not kw:
+            assert torch.equal(fa, fb)
+
+
 def test_clip_stream_matches_resident_decode():
     """Host-buffer front end (double-buffered copy-in / decode / copy-out): five different clips through two slots
     give the frames of the plain resident decode of each clip, in order."""
