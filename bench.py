@@ -241,7 +241,9 @@ def main():
 
     # e2e at N > 1: the clip sits in pinned host memory that every rank can read (here: every rank pins the same synthetic clip);
     # each rank copies 1 / N of it over its own PCIe link and the parts are all-gathered over NVLink (ClipStream.sliced_copy_in)
-    stream = ClipStream(dec, depth=2, distributed=world > 1, src=0, return_flow=True, sliced_copy_in=world > 1)
+    # (with destination row bands even that exchange is unnecessary: every rank pulls only the LR rows its band and halo read,
+    #  ClipStream.band_copy_in -- no collective on the end-to-end arm)
+    stream = ClipStream(dec, depth=2, distributed=world > 1, src=0, return_flow=True, sliced_copy_in=world > 1, band_copy_in=world > 1)
     lat_shapes = tuple(tuple(t.shape) for t in (feat_h, ff_h, res_h))
     rgb_dev = torch.empty(N, B, 3, HH, WW, dtype=torch.float32, device=dev)
     exchange = sharding.LatentExchange(lat_shapes, dev, src=0) if world > 1 else None
@@ -336,6 +338,9 @@ def main():
     value = clips * units_per_step * args.steps / (ms * 1e-3)
     e2e_value = clips * units_per_step * args.steps / (ms_e2e * 1e-3)
     h2d = clips * (feat_h.numel() + ff_h.numel() + res_h.numel()) * 4
+    if world > 1:  # every rank pulled the LR rows of its own band and halo (the halos overlap, so the sum exceeds one clip)
+        rows = sum(b - a for a, b in (SpaceTimeDecoder.lr_rows_of_band(H, HH, band_r, HALO) for band_r in sharding.partition_rows(HH, world) if band_r[1] > band_r[0]))
+        h2d = 5 * B * 64 * rows * W * 4
     d2h = clips * N * B * 3 * qs * 4  # all ranks together (each copies its own rows / clip out)
 
     # ---- roofline of the dominant kernel of the step (per launch, CUDA events on the launch stream) ----
@@ -438,7 +443,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                 "api": ("ClipStream.submit: copy-in, decode and copy-out of consecutive clips overlap on three streams (depth 2); every clip's own copies are inside the timed region"
-                        + ("; every rank copies 1/N of the clip's latents over its own PCIe link, in-place NCCL all-gather over NVLink, and copies its own band of the frames out" if world > 1 else ""))},
+                        + ("; every rank pulls the LR rows of its own band (+ halo) out of the pinned clip over its own PCIe link (strided copy, no collective) and copies its own band of the frames out" if world > 1 else ""))},
         "gpu_launches": launches, "halo_check": halo_check,
         "roofline": roofline, "roofline_splat": roofline_splat, "kernels": kernels,
         "cpu_baseline": cpu_baseline,

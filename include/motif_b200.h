@@ -36,6 +36,9 @@ const char* motif_last_error(void);
  * (process-wide; used by bench.py for its `gpu_launches` claim). */
 long long motif_launch_count(void);
 void motif_reset_launch_count(void);
+/* Strided copy between pinned host memory and the device on a stream (cudaMemcpy2DAsync): height runs of width bytes.  Plumbing of
+ * the multi-GPU host-buffer pipeline (motif_b200/clip_stream.py): a rank pulls only the LR rows its destination row band reads. */
+int motif_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, int to_device, void* stream);
 /* Optional per-kernel timing: when enabled, the library brackets each of its main kernels with
  * CUDA events on the launch stream.  motif_prof_collect() synchronises the device and sums the
  * recorded durations (ms) and launch counts for the kernel names given; returns the number of

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libmotif_b200.so")
 # every symbol include/motif_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "motif_abi_version",
+    "motif_memcpy2d_async",
     "motif_last_error",
     "motif_launch_count",
     "motif_reset_launch_count",
@@ -94,6 +95,8 @@ _lib = None
 
 def _declare(lib):
     lib.motif_abi_version.restype = c_int
+    lib.motif_memcpy2d_async.restype = c_int
+    lib.motif_memcpy2d_async.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_void_p]
     lib.motif_last_error.restype = c_char_p
     lib.motif_launch_count.restype = c_longlong
     lib.motif_reset_launch_count.restype = None

@@ -18,6 +18,10 @@ that share out.
 pulls the whole clip through its own PCIe link -- at 8 GPUs that copy (1.3 ms for the 73.7 MB of an Adobe clip) is longer than the
 1.2 ms band decode -- but every rank copies 1 / world_size of the flat latent buffer over ITS OWN link and the parts are
 all-gathered over NVLink (in place, on the copy-in stream, behind the previous clip's decode).
+
+``band_copy_in=True`` (same assumption, destination row bands): no collective at all -- a band decode reads only the LR rows of its
+band and halo (``SpaceTimeDecoder.lr_rows_of_band``: 18 % of the clip at 8 ranks), so every rank pulls exactly those rows of the three
+NCHW tensors out of the pinned host memory with one strided copy each (``motif_memcpy2d_async``) over its own PCIe link.
 """
 from __future__ import annotations
 
@@ -31,7 +35,7 @@ from .sharding import all_gather_slices, slice_plan
 
 class ClipStream:
     def __init__(self, decoder: SpaceTimeDecoder, depth: int = 2, distributed: bool = False, src: int = 0, group=None, return_flow: bool = False,
-                 sliced_copy_in: bool = False):
+                 sliced_copy_in: bool = False, band_copy_in: bool = False):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.dec = decoder
@@ -41,6 +45,7 @@ class ClipStream:
         self.src = src
         self.group = group
         self.sliced = bool(sliced_copy_in and distributed)
+        self.band_rows_only = bool(band_copy_in)
         self.return_flow = return_flow  # also produce the forward's second output (flow / 20 / (HH/H), Ours.py:858) on the device
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
@@ -81,7 +86,8 @@ class ClipStream:
         device).  Returns the device frame buffer ``[N, B, 3, HH, WW]`` of this slot (valid until the slot is reused)."""
         import torch.distributed as dist
 
-        is_src = (not self.distributed) or self.sliced or dist.get_rank(self.group) == self.src
+        band_pull = self.band_rows_only and row_range is not None
+        is_src = (not self.distributed) or self.sliced or band_pull or dist.get_rank(self.group) == self.src
         if is_src:
             shapes = tuple(tuple(t.shape) for t in (feat_h, flow_feat_h, residual_h))
         elif shapes is None:
@@ -98,7 +104,20 @@ class ClipStream:
         with torch.cuda.stream(self.s_in):
             if sl["ev_free"] is not None:
                 self.s_in.wait_event(sl["ev_free"])            # the decode that last read these buffers has finished
-            if self.sliced:
+            if band_pull:
+                # only the LR rows this rank's band (+ halo) can select, straight from the pinned NCHW tensors: no collective
+                from . import _lib
+
+                lib = _lib.load()
+                H, W = shapes[2][2], shapes[2][3]
+                lr0, lr1 = self.dec.lr_rows_of_band(H, HH, (r0, r1), halo)
+                if lr1 > lr0:
+                    for dst, src_t in zip(sl["lat"], (feat_h, flow_feat_h, residual_h)):
+                        planes, pitch = src_t.shape[0] * src_t.shape[1], H * W * 4
+                        rc = lib.motif_memcpy2d_async(dst.data_ptr() + lr0 * W * 4, pitch, src_t.data_ptr() + lr0 * W * 4, pitch, (lr1 - lr0) * W * 4, planes, 1,
+                                                      self.s_in.cuda_stream)
+                        _lib.check(rc, "motif_memcpy2d_async")
+            elif self.sliced:
                 # this rank's 1 / world of the flat buffer over its own PCIe link, then an in-place all-gather over NVLink
                 hosts = (feat_h, flow_feat_h, residual_h)
                 per, parts = slice_plan([t.numel() for t in hosts], self._world(), dist.get_rank(self.group))

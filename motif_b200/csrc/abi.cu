@@ -77,6 +77,16 @@ extern "C" const char* motif_last_error(void) { return g_last_error; }
 extern "C" long long motif_launch_count(void) { return g_launches.load(); }
 extern "C" void motif_reset_launch_count(void) { g_launches.store(0); }
 
+// Strided host <-> device copy on a stream (cudaMemcpy2DAsync): `height` runs of `width` bytes, `spitch` / `dpitch` bytes apart.
+// The host-buffer pipeline uses it to pull only the LR rows a destination row band reads out of pinned NCHW latents.
+extern "C" int motif_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, int to_device,
+                                    void* stream) {
+  MOTIF_REQUIRE(dst && src && width > 0 && height > 0 && dpitch >= width && spitch >= width, "memcpy2d: bad arguments");
+  MOTIF_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int motif_decode(const motif_decode_t* args, void* stream) {
   if (int rc = check_decode(args)) return rc;
   if (args->local_ensemble != 0 && args->precision == MOTIF_PRECISION_TF32X3)

@@ -344,6 +344,37 @@ def test_f16x3_timestamp_groups_and_rearmed_workspace():
     assert (part[6:10] - rgb1[6:10]).abs().max().item() < 1e-5
 
 
+def test_clip_stream_band_copy_in_pulls_only_the_bands_rows():
+    """``ClipStream(band_copy_in=True)``: a band decode from host buffers copies only the LR rows its band and halo read (one strided
+    copy per tensor, ``motif_memcpy2d_async``) -- the rest of the device latents stays whatever it was (poisoned here) -- and equals the
+    resident band decode."""
+    from motif_b200 import synthetic
+    from motif_b200.clip_stream import ClipStream
+    from motif_b200.decoder import SpaceTimeDecoder
+
+    params = decoder_ref.random_params(seed=5, **decoder_ref.REALISTIC)
+    dec = SpaceTimeDecoder(params, device="cuda", precision="f16x3")
+    H, W, HH, WW = 24, 40, 96, 160
+    hosts = [t.pin_memory() for t in synthetic.synthetic_latents(1, H, W, seed=4)]
+    tt = torch.tensor([[0.25, 0.75]])
+    band, halo = (32, 64), 16
+    want, _ = dec.decode(*[t.cuda() for t in hosts], tt, (HH, WW), row_range=band, halo=halo)
+    want = want[:, :, :, band[0]:band[1]].clone()
+    cs = ClipStream(dec, depth=2, band_copy_in=True)
+    out_h = torch.empty(2, 1, 3, band[1] - band[0], WW).pin_memory()
+    for k in range(3):  # the slots are reused: poison them between clips
+        for sl in cs._slots:
+            if sl is not None:
+                sl["flat"].fill_(float("nan"))
+        cs.submit(*hosts, tt, (HH, WW), out_h, row_range=band, halo=halo)
+        cs.synchronize()
+        assert torch.isfinite(out_h).all()
+        assert (out_h.cuda() - want).abs().max().item() < 1e-5
+    lr0, lr1 = dec.lr_rows_of_band(H, HH, band, halo)
+    lat = cs._slots[0]["lat"][0]
+    assert torch.isnan(lat[:, :, :lr0]).all() and torch.isnan(lat[:, :, lr1:]).all() and torch.isfinite(lat[:, :, lr0:lr1]).all()
+
+
 def test_nchw_latents_equal_the_packed_form():
     """f16x3 reads the reference's NCHW latents directly (motif_decode_t.latents_nchw); the pixel-major form the C ABI also accepts
     (motif_pack_latents) must give the same flows bit for bit and the same frames -- the per-LR-pixel tables see the same numbers in the
